@@ -1,0 +1,391 @@
+// C ABI of libb200rx.so (include/b200rx.h): handle, device scratch, stream plumbing, stage timing.
+// No CPU implementation of any stage exists in this library: without a CUDA device every entry
+// point fails.
+#include "rx_internal.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+using namespace b200rx;
+
+static thread_local std::string g_create_error;
+
+struct b200rx_handle {
+    int device = 0;
+    b200rx_limits limits{};
+    uint32_t max_steps = 0;  // trellis capacity per frame (multiple of 32)
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+
+    // device scratch
+    FrameDesc *desc = nullptr;
+    uint32_t *bm = nullptr;
+    uint2 *dec = nullptr;
+    unsigned long long *counters = nullptr; // 4 words
+
+    // staging for the host-buffer entry point (grow-only)
+    double *d_iq = nullptr; size_t d_iq_cap = 0;
+    uint64_t *d_lts1 = nullptr;
+    uint32_t *d_avail = nullptr;
+    uint8_t *d_payload = nullptr; size_t d_payload_cap = 0;
+    uint16_t *d_len = nullptr;
+    uint8_t *d_rate = nullptr;
+    uint8_t *d_status = nullptr;
+
+    uint64_t launches = 0;
+    std::string error;
+};
+
+namespace {
+
+int fail(b200rx_handle *h, int code, const char *what, cudaError_t ce = cudaSuccess)
+{
+    char buf[512];
+    if (ce != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString(ce), cudaGetErrorName(ce));
+    else snprintf(buf, sizeof(buf), "%s", what);
+    if (h) h->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(h, call)                                                         \
+    do {                                                                    \
+        cudaError_t ce_ = (call);                                           \
+        if (ce_ != cudaSuccess) return fail(h, B200RX_E_CUDA, #call, ce_);  \
+    } while (0)
+
+// ---- constant tables (regenerated from their defining rules; pinned by tests against the reference) ----
+bool g_tables_uploaded[64] = {false};
+
+} // namespace
+
+namespace b200rx {
+// defined next to the kernels that own the __constant__ symbols
+cudaError_t upload_frontend_tables(const double2 *tw, const int8_t *pol);
+cudaError_t upload_viterbi_tables(const uint32_t *crc, const uint8_t *scr);
+}
+
+cudaError_t b200rx::upload_tables()
+{
+    // twiddles exp(-2 pi i k / 64), built with exact octant symmetry
+    double2 tw[64];
+    for (int k = 0; k < 64; k++) {
+        const int q = k % 16, quad = k / 16;
+        double c, s;
+        if (q == 0) { c = 1.0; s = 0.0; }
+        else if (q == 8) { c = s = sqrt(0.5); }
+        else if (q < 8) { c = cos(2.0 * M_PI * q / 64.0); s = sin(2.0 * M_PI * q / 64.0); }
+        else { c = sin(2.0 * M_PI * (16 - q) / 64.0); s = cos(2.0 * M_PI * (16 - q) / 64.0); }
+        double re, im; // exp(+i theta)
+        switch (quad) {
+            case 0: re = c; im = s; break;
+            case 1: re = -s; im = c; break;
+            case 2: re = -c; im = -s; break;
+            default: re = s; im = -c; break;
+        }
+        tw[k] = make_double2(re, -im);
+    }
+    // pilot polarity: 802.11a 17.3.5.9, scrambler x^7 + x^4 + 1 from the all-ones state, 0 -> +1, 1 -> -1
+    int8_t pol[127];
+    int st = 0x7F;
+    for (int i = 0; i < 127; i++) {
+        const int fb = ((st >> 6) ^ (st >> 3)) & 1;
+        st = ((st << 1) | fb) & 0x7F;
+        pol[i] = fb ? -1 : 1;
+    }
+    cudaError_t e = upload_frontend_tables(tw, pol);
+    if (e != cudaSuccess) return e;
+
+    // CRC-32/ISO-HDLC slice-by-4 tables
+    static uint32_t crc[4][256];
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+        crc[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; i++)
+        for (int t = 1; t < 4; t++) crc[t][i] = (crc[t - 1][i] >> 8) ^ crc[0][crc[t - 1][i] & 0xFF];
+    // descrambler: ppdu.cpp:257-263, state 93, feedback = bit6 ^ bit3, one step per byte
+    uint8_t scr[127];
+    int state = 93;
+    for (int x = 0; x < 127; x++) {
+        const int fb = ((state >> 6) & 1) ^ ((state >> 3) & 1);
+        scr[x] = (uint8_t)fb;
+        state = ((state << 1) & 0x7E) | fb;
+    }
+    return upload_viterbi_tables(&crc[0][0], scr);
+}
+
+extern "C" {
+
+const char *b200rx_version(void) { return "b200rx 0.1 (sm_100a)"; }
+
+const char *b200rx_last_error(const b200rx_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
+{
+    if (!out || !limits) return fail(nullptr, B200RX_E_ARG, "b200rx_create: null argument");
+    *out = nullptr;
+    if (limits->max_frames == 0 || limits->max_payload_bytes > 4095)
+        return fail(nullptr, B200RX_E_ARG, "b200rx_create: limits out of range");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, B200RX_E_DEVICE, "b200rx_create: no CUDA device (this library has no CPU path)", ce);
+    if (device < 0 || device >= ndev) return fail(nullptr, B200RX_E_ARG, "b200rx_create: bad device index");
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "b200rx_create: device %d is sm_%d%d; the kernels are built for sm_100a only", device,
+                 prop.major, prop.minor);
+        return fail(nullptr, B200RX_E_DEVICE, buf);
+    }
+    CU(nullptr, cudaSetDevice(device));
+    if (!g_tables_uploaded[device & 63]) {
+        CU(nullptr, upload_tables());
+        g_tables_uploaded[device & 63] = true;
+    }
+
+    b200rx_handle *h = new (std::nothrow) b200rx_handle();
+    if (!h) return fail(nullptr, B200RX_E_NOMEM, "b200rx_create: out of host memory");
+    h->device = device;
+    h->limits = *limits;
+    h->max_steps = max_steps_for(limits->max_payload_bytes);
+    const size_t nf = limits->max_frames;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
+    A((void **)&h->desc, nf * sizeof(FrameDesc));
+    A((void **)&h->bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
+    A((void **)&h->dec, nf * (size_t)h->max_steps * sizeof(uint2));
+    A((void **)&h->counters, 4 * sizeof(unsigned long long));
+    A((void **)&h->d_lts1, nf * sizeof(uint64_t));
+    A((void **)&h->d_avail, nf * sizeof(uint32_t));
+    A((void **)&h->d_len, nf * sizeof(uint16_t));
+    A((void **)&h->d_rate, nf);
+    A((void **)&h->d_status, nf);
+    if (e != cudaSuccess) {
+        int code = (e == cudaErrorMemoryAllocation) ? B200RX_E_NOMEM : B200RX_E_CUDA;
+        fail(nullptr, code, "b200rx_create: allocating device scratch", e);
+        b200rx_destroy(h);
+        return code;
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return B200RX_OK;
+}
+
+int b200rx_destroy(b200rx_handle *h)
+{
+    if (!h) return B200RX_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->desc); cudaFree(h->bm); cudaFree(h->dec); cudaFree(h->counters);
+    cudaFree(h->d_iq); cudaFree(h->d_lts1); cudaFree(h->d_avail); cudaFree(h->d_payload);
+    cudaFree(h->d_len); cudaFree(h->d_rate); cudaFree(h->d_status);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return B200RX_OK;
+}
+
+int b200rx_set_stream(b200rx_handle *h, void *cuda_stream)
+{
+    if (!h) return B200RX_E_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return B200RX_OK;
+}
+
+int b200rx_synchronize(b200rx_handle *h)
+{
+    if (!h) return B200RX_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return B200RX_OK;
+}
+
+int b200rx_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return B200RX_E_ARG;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { *ptr = nullptr; return fail(nullptr, B200RX_E_NOMEM, "b200rx_host_alloc", e); }
+    return B200RX_OK;
+}
+
+int b200rx_host_free(void *ptr)
+{
+    if (!ptr) return B200RX_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? B200RX_OK : B200RX_E_CUDA;
+}
+
+uint64_t b200rx_launch_count(const b200rx_handle *h) { return h ? h->launches : 0; }
+uint32_t b200rx_max_steps(const b200rx_handle *h) { return h ? h->max_steps : 0; }
+
+int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_samples,
+                            const uint64_t *lts1_index_dev, const uint32_t *avail_dev, uint32_t n_frames,
+                            uint8_t *payload_out_dev, uint32_t payload_stride,
+                            uint16_t *payload_len_dev, uint8_t *rate_out_dev, uint8_t *status_dev,
+                            const b200rx_debug *dbg)
+{
+    if (!h) return B200RX_E_ARG;
+    if (!iq_dev || !lts1_index_dev || !avail_dev || !status_dev)
+        return fail(h, B200RX_E_ARG, "b200rx_decode_batch_dev: null argument");
+    if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_batch_dev: n_frames exceeds max_frames");
+    if (n_frames == 0) return B200RX_OK;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+
+    CU(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), s));
+    CU(h, cudaEventRecord(h->ev[0], s));
+
+    FrontendArgs fa{};
+    fa.iq = reinterpret_cast<const double2 *>(iq_dev);
+    fa.iq_samples = iq_samples;
+    fa.lts1 = lts1_index_dev;
+    fa.avail = avail_dev;
+    fa.n_frames = n_frames;
+    fa.desc = h->desc;
+    fa.bm = h->bm;
+    fa.bm_stride = h->max_steps;
+    fa.max_steps = h->max_steps;
+    fa.max_len = h->limits.max_payload_bytes;
+    if (dbg) {
+        fa.dbg_eq = reinterpret_cast<double2 *>(dbg->equalized);
+        fa.dbg_eq_vectors = dbg->eq_vectors;
+        fa.dbg_depunct = dbg->depunct;
+        fa.dbg_depunct_stride = dbg->depunct_stride;
+    }
+    CU(h, launch_frontend(fa, s));
+    CU(h, cudaEventRecord(h->ev[1], s));
+    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, h->max_steps, n_frames, s));
+    CU(h, cudaEventRecord(h->ev[2], s));
+
+    TracebackArgs ta{};
+    ta.desc = h->desc;
+    ta.dec = h->dec;
+    ta.dec_stride = h->max_steps;
+    ta.n_frames = n_frames;
+    ta.raw_mode = 0;
+    ta.payload = payload_out_dev;
+    ta.payload_stride = payload_stride;
+    ta.payload_len = payload_len_dev;
+    ta.rate_out = rate_out_dev;
+    ta.status_out = status_dev;
+    ta.counters = h->counters;
+    if (dbg) {
+        ta.dbg_decoded = dbg->decoded;
+        ta.dbg_decoded_stride = dbg->decoded_stride;
+        ta.dbg_field = dbg->header_field;
+    }
+    CU(h, launch_traceback(ta, s));
+    CU(h, cudaEventRecord(h->ev[3], s));
+    h->ev_valid = true;
+    h->launches += 3;
+    return B200RX_OK;
+}
+
+int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
+                        const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
+                        uint8_t *payload_out, uint32_t payload_stride,
+                        uint16_t *payload_len, uint8_t *rate_out, uint8_t *status)
+{
+    if (!h) return B200RX_E_ARG;
+    if (!iq || !lts1_index || !avail || !status) return fail(h, B200RX_E_ARG, "b200rx_decode_batch: null argument");
+    if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_batch: n_frames exceeds max_frames");
+    if (n_frames == 0) return B200RX_OK;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+
+    const size_t iq_bytes = (size_t)iq_samples * 2 * sizeof(double);
+    if (iq_bytes > h->d_iq_cap) {
+        if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_decode_batch: sample staging", e);
+        h->d_iq_cap = iq_bytes;
+    }
+    const size_t pl_bytes = payload_out ? (size_t)n_frames * payload_stride : 0;
+    if (pl_bytes > h->d_payload_cap) {
+        if (h->d_payload) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_payload); h->d_payload = nullptr; h->d_payload_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->d_payload, pl_bytes);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_decode_batch: payload staging", e);
+        h->d_payload_cap = pl_bytes;
+    }
+    CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    int rc = b200rx_decode_batch_dev(h, h->d_iq, iq_samples, h->d_lts1, h->d_avail, n_frames,
+                                     payload_out ? h->d_payload : nullptr, payload_stride, h->d_len, h->d_rate,
+                                     h->d_status, nullptr);
+    if (rc != B200RX_OK) return rc;
+    if (payload_out) CU(h, cudaMemcpyAsync(payload_out, h->d_payload, pl_bytes, cudaMemcpyDeviceToHost, s));
+    if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+    if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, n_frames, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(status, h->d_status, n_frames, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    return B200RX_OK;
+}
+
+int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint64_t symbols_stride,
+                             const uint32_t *data_bits_dev, uint32_t max_data_bits, uint32_t n_frames,
+                             uint8_t *out_dev, uint32_t out_stride)
+{
+    if (!h) return B200RX_E_ARG;
+    if (!symbols_dev || !data_bits_dev || !out_dev) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: null argument");
+    if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: n_frames exceeds max_frames");
+    if (max_data_bits + 6 > h->max_steps) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: trellis longer than the handle's capacity");
+    if ((symbols_stride & 1) || ((uintptr_t)symbols_dev & 1)) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: symbols must be 2-byte aligned");
+    if (n_frames == 0) return B200RX_OK;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), s));
+    CU(h, cudaEventRecord(h->ev[0], s));
+    CU(h, launch_bm_from_symbols(symbols_dev, symbols_stride, data_bits_dev, max_data_bits, n_frames, h->desc, h->bm,
+                                 h->max_steps, h->max_steps, s));
+    CU(h, cudaEventRecord(h->ev[1], s));
+    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, h->max_steps, n_frames, s));
+    CU(h, cudaEventRecord(h->ev[2], s));
+    TracebackArgs ta{};
+    ta.desc = h->desc;
+    ta.dec = h->dec;
+    ta.dec_stride = h->max_steps;
+    ta.n_frames = n_frames;
+    ta.raw_mode = 1;
+    ta.payload = out_dev;
+    ta.payload_stride = out_stride;
+    ta.counters = h->counters;
+    CU(h, launch_traceback(ta, s));
+    CU(h, cudaEventRecord(h->ev[3], s));
+    h->ev_valid = true;
+    h->launches += 3;
+    return B200RX_OK;
+}
+
+int b200rx_get_stats(b200rx_handle *h, b200rx_stats *out)
+{
+    if (!h || !out) return B200RX_E_ARG;
+    memset(out, 0, sizeof(*out));
+    if (!h->ev_valid) return B200RX_OK;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaEventElapsedTime(&out->frontend_ms, h->ev[0], h->ev[1]));
+    CU(h, cudaEventElapsedTime(&out->viterbi_ms, h->ev[1], h->ev[2]));
+    CU(h, cudaEventElapsedTime(&out->traceback_ms, h->ev[2], h->ev[3]));
+    CU(h, cudaEventElapsedTime(&out->total_ms, h->ev[0], h->ev[3]));
+    unsigned long long c[4];
+    CU(h, cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out->frames_ok = (uint32_t)c[0];
+    out->frames_failed = (uint32_t)c[1];
+    out->payload_bytes = c[2];
+    out->trellis_steps = c[3];
+    return B200RX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,318 @@
+// Front end of the batched receive path: everything the reference does between the tagged sample
+// stream and the Viterbi decoder, fused into one kernel so that no intermediate touches HBM:
+//
+//   fft_symbols::work   (src/fft_symbols.cpp:33-80)   CP strip + 64-point forward FFT, shifted order
+//   channel_est::work   (src/channel_est.cpp:36-85)   H^-1 = mean of the two LTS inverses; equalise
+//   phase_tracker::work (src/phase_tracker.cpp:70-105) 4-pilot common phase, derotate, keep 48 carriers
+//   ppdu::decode_header (src/ppdu.cpp:168-218)        SIGNAL: BPSK demap, deinterleave, 24-step Viterbi
+//   modulator::demodulate (src/modulator.cpp:108-164, src/qam.h:110-125)   soft bits 0..255
+//   interleaver::deinterleave (src/interleaver.cpp:28-38)                  48-element permutation
+//   puncturer::depuncture (src/puncturer.cpp:78-123)                       erasures = 127
+//   + the branch-metric arithmetic of viterbi.cpp:234-248 (4 distinct values per trellis step)
+//
+// One CTA per frame, one warp per OFDM symbol.  A warp loads the 64 useful samples of its symbol with
+// one coalesced 16-byte load per lane pair (2 samples per lane), runs the FFT in registers
+// (radix-2 DIF, 1 in-lane + 5 shuffle stages), and hands the bins to the rest of the warp through a
+// 1 KB shared-memory tile.  HBM traffic per symbol: 1024 B of samples in, 4*dbps B of branch metrics out.
+// All arithmetic before the quantiser is fp64 like the reference.
+#include "rx_internal.cuh"
+#include "viterbi_core.cuh"
+
+#include <math.h>
+
+namespace b200rx {
+
+namespace {
+
+constexpr int FE_WARPS = 8;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__constant__ double2 c_twiddle[64];  // exp(-2 pi i k / 64)
+__constant__ int8_t c_polarity[127]; // pilot polarity sequence (phase_tracker.cpp:23-32)
+
+// LTS_FREQ_DOMAIN (preamble.h:363-429; IEEE 802.11a 17.3.3 L_{-26..26}), index s <-> subcarrier s - 32.
+// Bit s of NONZERO: carrier is used; bit s of NEG: value is -1.
+// (pinned against the reference's table by tests/test_tables.py)
+constexpr unsigned long long LTS_NONZERO = 0x07FFFFFEFFFFFFC0ull;
+constexpr unsigned long long LTS_NEG = 0x00567D4C0A605300ull;
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 shfl_xor2(double2 v, int m)
+{
+    return make_double2(__shfl_xor_sync(FULL, v.x, m), __shfl_xor_sync(FULL, v.y, m));
+}
+
+// 64-point forward DFT of (v0, v1) = (x[lane], x[lane + 32]).  On return lane holds
+// X[k0] in v0 and X[k1] in v1 with k = bitrev6((lane << 1) | slot); in the reference's shifted
+// storage (fft.cpp:20-24: data[s] = X[(s + 32) % 64]) that is s = ((slot ^ 1) << 5) | bitrev5(lane).
+__device__ __forceinline__ void warp_fft64(double2 &v0, double2 &v1, const double2 *tw, int lane)
+{
+    double2 a = v0, b = v1;
+    v0 = cadd(a, b);
+    v1 = cmul(csub(a, b), tw[lane]);
+#pragma unroll
+    for (int bb = 4; bb >= 0; --bb) {
+        const int S = 1 << bb;
+        const bool hi = (lane & S) != 0;
+        const double2 send = hi ? v0 : v1;
+        const double2 recv = shfl_xor2(send, S);
+        a = hi ? recv : v0;
+        b = hi ? v1 : recv;
+        v0 = cadd(a, b);
+        const double2 d = csub(a, b);
+        v1 = (bb > 0) ? cmul(d, tw[(lane & (S - 1)) << (5 - bb)]) : d;
+    }
+}
+
+__device__ __forceinline__ int shifted_index(int lane, int slot) { return ((slot ^ 1) << 5) | (int)(__brev((unsigned)lane) >> 27); }
+
+// 48 data carriers in ascending bin order (phase_tracker.cpp:46-50): 6..58 without 11, 25, 32, 39, 53
+__device__ __forceinline__ int data_bin(int c)
+{
+    return c + 6 + (c >= 5) + (c >= 18) + (c >= 24) + (c >= 30) + (c >= 43);
+}
+
+// QAM<N>::decode (qam.h:110-125) for one axis: pt = (int)(x * scale) truncates toward zero
+template <int NBITS>
+__device__ __forceinline__ void qam_decode_axis(double x, double scale, uint8_t *bits)
+{
+    int pt = __double2int_rz(x * scale);
+    int flip = 1;
+    int amp = (1 << (NBITS - 1)) << (8 - NBITS);
+#pragma unroll
+    for (int i = 0; i < NBITS; i++) {
+        int v = flip * pt + 128;
+        bits[i] = (uint8_t)min(max(v, 0), 255);
+        const int sgn = pt < 0 ? -1 : 1;
+        pt -= sgn * amp;
+        flip = -sgn;
+        amp >>= 1;
+    }
+}
+
+// d_scale_d of qam.h:50 for the four constellations the reference instantiates (modulator.cpp:120-153)
+__device__ __forceinline__ double demap_scale(int bpsc)
+{
+    switch (bpsc) {
+        case 1: return 128.0;                         // QAM<1>(1.0): 2^7 / sqrt(1)
+        case 2: return 128.0 / sqrt(0.5);             // QAM<1>(0.5): 2^7 / sqrt(0.5)
+        case 4: return 64.0 / sqrt(0.5 * 2.0 / 10.0); // QAM<2>(0.5): 2^6 / sqrt(0.5 * 2 / 10)
+        default: return 32.0 / sqrt(0.5 * 4.0 / 84.0); // QAM<3>(0.5): 2^5 / sqrt(0.5 * 4 / 84)
+    }
+}
+
+// Deinterleaved soft bit k of the current OFDM symbol (interleaver.cpp:31-37: BitInterleave(48, 1) always):
+// out[blk + k'] = in[blk + 3 * (k' % 16) + k' / 16]
+__device__ __forceinline__ uint32_t deint_at(const uint8_t *soft, int k)
+{
+    const int blk = (k / 48) * 48, kk = k - blk;
+    return soft[blk + 3 * (kk & 15) + (kk >> 4)];
+}
+
+// The two depunctured soft symbols of trellis step t (0-based within the OFDM symbol), puncturer.cpp:94-118
+__device__ __forceinline__ void step_symbols(const uint8_t *soft, int punc, int t, uint32_t &s0, uint32_t &s1)
+{
+    if (punc == PUNC_1_2) {
+        s0 = deint_at(soft, 2 * t);
+        s1 = deint_at(soft, 2 * t + 1);
+    } else if (punc == PUNC_3_4) { // d0 d1 127 d2 127 d3 per 4 coded bits -> 3 steps
+        const int g = t / 3, r = t - 3 * g;
+        if (r == 0) { s0 = deint_at(soft, 4 * g); s1 = deint_at(soft, 4 * g + 1); }
+        else if (r == 1) { s0 = 127u; s1 = deint_at(soft, 4 * g + 2); }
+        else { s0 = 127u; s1 = deint_at(soft, 4 * g + 3); }
+    } else { // d0 127 d1 d2 per 3 coded bits -> 2 steps
+        const int g = t >> 1;
+        if ((t & 1) == 0) { s0 = deint_at(soft, 3 * g); s1 = 127u; }
+        else { s0 = deint_at(soft, 3 * g + 1); s1 = deint_at(soft, 3 * g + 2); }
+    }
+}
+
+struct SymbolCtx {
+    const double2 *tw;   // smem twiddles
+    const double2 *hinv; // smem inverse channel
+    double2 *xs;         // smem, this warp's 64 bins (shifted order)
+    uint8_t *soft;       // smem, this warp's soft bits (up to 288)
+};
+
+// One OFDM symbol: samples -> equalised, derotated data carriers -> soft bits in ctx.soft.
+// v = symbol index from SIGNAL (0) on: selects the pilot polarity (phase_tracker.cpp:77-86).
+__device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const double2 *win, int v, int bpsc, int lane,
+                                               double2 *dbg_eq)
+{
+    double2 v0 = win[lane], v1 = win[lane + 32];
+    warp_fft64(v0, v1, ctx.tw, lane);
+    ctx.xs[shifted_index(lane, 0)] = v0;
+    ctx.xs[shifted_index(lane, 1)] = v1;
+    __syncwarp();
+
+    // phase_tracker.cpp:83-92: e = sum_p rec_p * conj(ref_p) / 4, ref_p = sign_p * POLARITY[v % 127] (real)
+    const double pol = (double)c_polarity[v % 127];
+    double2 e = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int bin = 11 + 14 * p;
+        const double ref = (p == 3) ? -pol : pol;
+        const double2 rec = cmul(ctx.hinv[bin], ctx.xs[bin]);
+        e.x += rec.x * ref / 4.0;
+        e.y += rec.y * ref / 4.0;
+    }
+    // phase_tracker.cpp:92-98 rotates by exp(-i arg(e)) = conj(e) / |e|
+    const double mag = hypot(e.x, e.y);
+    const double2 rot = (mag > 0.0) ? make_double2(e.x / mag, -e.y / mag) : make_double2(1.0, 0.0);
+
+    const double scale = demap_scale(bpsc);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int c = lane + 32 * h;
+        if (c < 48) {
+            const int bin = data_bin(c);
+            const double2 y = cmul(cmul(ctx.hinv[bin], ctx.xs[bin]), rot);
+            if (dbg_eq) dbg_eq[c] = y;
+            uint8_t *o = ctx.soft + c * bpsc;
+            switch (bpsc) { // modulator.cpp:118-160: real axis first, then imaginary
+                case 1: qam_decode_axis<1>(y.x, scale, o); break;
+                case 2: qam_decode_axis<1>(y.x, scale, o); qam_decode_axis<1>(y.y, scale, o + 1); break;
+                case 4: qam_decode_axis<2>(y.x, scale, o); qam_decode_axis<2>(y.y, scale, o + 2); break;
+                default: qam_decode_axis<3>(y.x, scale, o); qam_decode_axis<3>(y.y, scale, o + 3); break;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
+{
+    __shared__ double2 s_tw[64];
+    __shared__ double2 s_hinv[64];
+    __shared__ double2 s_xs[FE_WARPS][64];
+    __shared__ uint8_t s_soft[FE_WARPS][288];
+    __shared__ uint32_t s_hdr_bm[32];
+    __shared__ FrameDesc s_desc;
+
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t p = a.lts1[frame];
+    uint32_t avail = a.avail[frame];
+    if (p >= a.iq_samples) avail = 0;
+    else if ((uint64_t)avail > a.iq_samples - p) avail = (uint32_t)(a.iq_samples - p);
+    const double2 *win = a.iq + p;
+
+    if (tid < 64) s_tw[tid] = c_twiddle[tid];
+    if (tid == 0) {
+        s_desc.n_steps = 0; s_desc.data_bits = 0; s_desc.field = 0; s_desc.length = 0;
+        s_desc.rate = B200RX_RATE_INVALID; s_desc.status = B200RX_ST_TRUNCATED;
+    }
+    __syncthreads();
+
+    // fft_symbols.cpp:42-71 with LTS1 at sample 0 and LTS2 at 64: windows [0,64) and [64,128);
+    // the SIGNAL symbol occupies [144, 208).  Nothing is decodable below 208 samples.
+    if (avail < 208) {
+        if (tid == 0) a.desc[frame] = s_desc;
+        return;
+    }
+
+    SymbolCtx ctx{s_tw, s_hinv, s_xs[warp], s_soft[warp]};
+
+    // ---- channel estimate: channel_est.cpp:53-58, H^-1[j] = sum_{2 LTS} L[j] / R[j] / 2 for all 64 bins ----
+    if (warp < 2) {
+        double2 v0 = win[64 * warp + lane], v1 = win[64 * warp + lane + 32];
+        warp_fft64(v0, v1, s_tw, lane);
+#pragma unroll
+        for (int slot = 0; slot < 2; slot++) {
+            const double2 r = slot ? v1 : v0;
+            const int s = shifted_index(lane, slot);
+            double l = ((LTS_NONZERO >> s) & 1ull) ? (((LTS_NEG >> s) & 1ull) ? -1.0 : 1.0) : 0.0;
+            // L / R with L real: L * conj(R) / |R|^2, then / 2
+            const double den = r.x * r.x + r.y * r.y;
+            s_xs[warp][s] = make_double2(l * r.x / den / 2.0, -l * r.y / den / 2.0);
+        }
+    }
+    __syncthreads();
+    if (tid < 64) s_hinv[tid] = cadd(s_xs[0][tid], s_xs[1][tid]);
+    __syncthreads();
+
+    // ---- SIGNAL: ppdu.cpp:168-218 ----
+    if (warp == 0) {
+        double2 *dbg = a.dbg_eq ? a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors) * 48 : nullptr;
+        process_symbol(ctx, win + 128 + 16, 0, 1, lane, (dbg && a.dbg_eq_vectors > 0) ? dbg : nullptr);
+        if (lane < 24) {
+            uint32_t s0, s1;
+            step_symbols(ctx.soft, PUNC_1_2, lane, s0, s1);
+            s_hdr_bm[lane] = bm_word(s0, s1);
+        }
+        __syncwarp();
+        // 18 data bits -> 24 trellis steps -> 3 bytes MSB first (ppdu.cpp:181-186)
+        const uint32_t field = warp_viterbi_short(s_hdr_bm, 24, 18, lane);
+        if (lane == 0) {
+            s_desc.field = field;
+            uint32_t x = field; // parity.h:43-48
+            x ^= x >> 16; x ^= x >> 8;
+            const int par = __popc(x & 0xFFu) & 1;
+            const int rate = rate_from_field((field >> 19) & 0xF); // ppdu.cpp:194
+            const uint32_t len = (field >> 6) & 0xFFF;             // ppdu.cpp:195
+            if (par) s_desc.status = B200RX_ST_HDR_PARITY;
+            else if (rate == 255) s_desc.status = B200RX_ST_HDR_RATE;
+            else {
+                const uint32_t nsym = num_symbols(rate, len);
+                const uint32_t steps = nsym * rate_row(rate).dbps;
+                s_desc.rate = (uint8_t)rate;
+                s_desc.length = (uint16_t)len;
+                if (len > a.max_len || steps > a.max_steps) s_desc.status = B200RX_ST_TOO_LONG;
+                else if ((uint64_t)avail < 128ull + 80ull * (1ull + nsym)) s_desc.status = B200RX_ST_TRUNCATED;
+                else {
+                    s_desc.status = B200RX_ST_OK;
+                    s_desc.n_steps = steps;
+                    s_desc.data_bits = steps - 6;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const FrameDesc d = s_desc;
+    if (tid == 0) a.desc[frame] = d;
+    if (d.status != B200RX_ST_OK) return;
+
+    // ---- data symbols ----
+    const RateRow rr = rate_row(d.rate);
+    const uint32_t nsym = d.n_steps / rr.dbps;
+    uint32_t *bm_out = a.bm + (size_t)frame * a.bm_stride;
+    for (uint32_t s = warp; s < nsym; s += FE_WARPS) {
+        double2 *dbg = nullptr;
+        if (a.dbg_eq && s + 1 < a.dbg_eq_vectors) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors + s + 1) * 48;
+        process_symbol(ctx, win + 128 + 80 * (size_t)(s + 1) + 16, (int)(s + 1), rr.bpsc, lane, dbg);
+        for (int t = lane; t < rr.dbps; t += 32) {
+            uint32_t s0, s1;
+            step_symbols(ctx.soft, rr.punc, t, s0, s1);
+            const size_t step = (size_t)s * rr.dbps + t;
+            bm_out[step] = bm_word(s0, s1);
+            if (a.dbg_depunct && 2 * step + 1 < a.dbg_depunct_stride) {
+                uint8_t *dp = a.dbg_depunct + (size_t)frame * a.dbg_depunct_stride + 2 * step;
+                dp[0] = (uint8_t)s0; dp[1] = (uint8_t)s1;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace
+
+cudaError_t upload_frontend_tables(const double2 *tw, const int8_t *pol)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_twiddle, tw, sizeof(double2) * 64);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_polarity, pol, 127);
+}
+
+cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s)
+{
+    if (a.n_frames == 0) return cudaSuccess;
+    frontend_kernel<<<a.n_frames, FE_WARPS * 32, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace b200rx

@@ -1,0 +1,155 @@
+// Internal declarations shared by the b200rx translation units (kernels + C ABI).
+// Device layout of everything that lives in HBM between kernels is defined here.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200rx.h"
+
+namespace b200rx {
+
+// ---- rate parameters (reference src/rates.h:52-196), indexed by fun::Rate value ----
+enum { PUNC_1_2 = 0, PUNC_2_3 = 1, PUNC_3_4 = 2 };
+
+struct RateRow { uint16_t cbps, dbps; uint8_t bpsc, punc, rate_field, pad; };
+
+__host__ __device__ __forceinline__ RateRow rate_row(int r)
+{
+    // cbps, dbps, bpsc, punc, rate_field
+    switch (r) {
+        case 0: return {48, 24, 1, PUNC_1_2, 0xD, 0};
+        case 1: return {48, 32, 1, PUNC_2_3, 0xE, 0};
+        case 2: return {48, 36, 1, PUNC_3_4, 0xF, 0};
+        case 3: return {96, 48, 2, PUNC_1_2, 0x5, 0};
+        case 4: return {96, 64, 2, PUNC_2_3, 0x6, 0};
+        case 5: return {96, 72, 2, PUNC_3_4, 0x7, 0};
+        case 6: return {192, 96, 4, PUNC_1_2, 0x9, 0};
+        case 7: return {192, 128, 4, PUNC_2_3, 0xA, 0};
+        case 8: return {192, 144, 4, PUNC_3_4, 0xB, 0};
+        case 9: return {288, 192, 6, PUNC_2_3, 0x1, 0};
+        default: return {288, 216, 6, PUNC_3_4, 0x3, 0};
+    }
+}
+
+// rate field (4 bits) -> fun::Rate, 255 when not in VALID_RATES (rates.h:21, :208-249)
+__host__ __device__ __forceinline__ int rate_from_field(int f)
+{
+    switch (f & 0xF) {
+        case 0xD: return 0; case 0xE: return 1; case 0xF: return 2;
+        case 0x5: return 3; case 0x6: return 4; case 0x7: return 5;
+        case 0x9: return 6; case 0xA: return 7; case 0xB: return 8;
+        case 0x1: return 9; case 0x3: return 10;
+        default: return 255;
+    }
+}
+
+// ppdu.cpp:38-40: ceil((16 + 8*(len + 4) + 6) / dbps)
+__host__ __device__ __forceinline__ uint32_t num_symbols(int rate, uint32_t length)
+{
+    const uint32_t dbps = rate_row(rate).dbps;
+    return (16u + 8u * (length + 4u) + 6u + dbps - 1u) / dbps;
+}
+
+// Largest trellis (steps) any rate needs for a payload of max_len bytes, rounded up to 32.
+inline uint32_t max_steps_for(uint32_t max_len)
+{
+    uint32_t m = 0;
+    for (int r = 0; r < 11; r++) {
+        uint32_t s = num_symbols(r, max_len) * rate_row(r).dbps;
+        if (s > m) m = s;
+    }
+    return (m + 31u) & ~31u;
+}
+
+// ---- per-frame descriptor written by the front end, read by the Viterbi and traceback kernels ----
+struct FrameDesc {
+    uint32_t n_steps;   // trellis steps = nsym * dbps (0 when the frame is not decoded)
+    uint32_t data_bits; // n_steps - 6: bits produced by the traceback (viterbi.cpp:31-37)
+    uint32_t field;     // 24-bit SIGNAL field as decoded
+    uint16_t length;    // LENGTH
+    uint8_t rate;       // fun::Rate or 255
+    uint8_t status;     // B200RX_ST_* so far (traceback turns OK into CRC_FAIL where needed)
+};
+
+// ---- branch-metric word (one per trellis step) ----
+// byte c = ((s0 ^ b0) + (s1 ^ b1) + 1) >> 3 with b0 = (c & 2) ? 255 : 0, b1 = (c & 1) ? 255 : 0:
+// the four distinct values pavgb/psrlw produce in viterbi.cpp:234-248 (Branchtab entries are 0 or 255).
+__host__ __device__ __forceinline__ uint32_t bm_word(uint32_t s0, uint32_t s1)
+{
+    const uint32_t n0 = s0 ^ 255u, n1 = s1 ^ 255u;
+    const uint32_t m00 = (s0 + s1 + 1u) >> 3;
+    const uint32_t m01 = (s0 + n1 + 1u) >> 3;
+    const uint32_t m10 = (n0 + s1 + 1u) >> 3;
+    const uint32_t m11 = (n0 + n1 + 1u) >> 3;
+    return m00 | (m01 << 8) | (m10 << 16) | (m11 << 24);
+}
+
+// Branch class of butterfly j (0..31): Branchtab[0][j] = parity(2j & 121), Branchtab[1][j] = parity(2j & 91)
+// (viterbi.cpp:87-91).  2j & 121 keeps j bits 2,3,4; 2j & 91 keeps j bits 0,2,3.
+__host__ __device__ __forceinline__ uint32_t branch_class(uint32_t j)
+{
+    const uint32_t b0 = ((j >> 2) ^ (j >> 3) ^ (j >> 4)) & 1u;
+    const uint32_t b1 = (j ^ (j >> 2) ^ (j >> 3)) & 1u;
+    return (b0 << 1) | b1;
+}
+
+// ---- survivor (decision) storage ----
+// One uint2 per trellis step: .x bit l = decision of new state 2l, .y bit l = decision of new state 2l+1
+// (decision 1 = survivor came from predecessor j+32, viterbi.cpp:256-273).
+__device__ __forceinline__ uint32_t decision_bit(const uint2 *dec, uint32_t t, uint32_t state)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(dec + t) + (state & 1u);
+    return (__ldg(w) >> (state >> 1)) & 1u;
+}
+
+// ---- launchers (each returns the cudaError_t of the launch) ----
+struct FrontendArgs {
+    const double2 *iq;
+    uint64_t iq_samples;
+    const uint64_t *lts1;
+    const uint32_t *avail;
+    uint32_t n_frames;
+    FrameDesc *desc;
+    uint32_t *bm;            // [n_frames][bm_stride] branch-metric words
+    uint32_t bm_stride;      // words per frame (>= max_steps, multiple of 32)
+    uint32_t max_steps;
+    uint32_t max_len;
+    // taps (may be null)
+    double2 *dbg_eq;
+    uint32_t dbg_eq_vectors;
+    uint8_t *dbg_depunct;
+    uint32_t dbg_depunct_stride;
+};
+
+cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s);
+
+cudaError_t launch_bm_from_symbols(const uint8_t *symbols, uint64_t symbols_stride, const uint32_t *data_bits,
+                                   uint32_t max_data_bits, uint32_t n_frames, FrameDesc *desc, uint32_t *bm,
+                                   uint32_t bm_stride, uint32_t max_steps, cudaStream_t s);
+
+cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride, uint2 *dec,
+                               uint32_t dec_stride, uint32_t n_frames, cudaStream_t s);
+
+struct TracebackArgs {
+    FrameDesc *desc;
+    const uint2 *dec;
+    uint32_t dec_stride;
+    uint32_t n_frames;
+    int raw_mode;            // 1: Viterbi-only entry point — write decoded bytes, no descramble/CRC
+    uint8_t *payload;
+    uint32_t payload_stride;
+    uint16_t *payload_len;
+    uint8_t *rate_out;
+    uint8_t *status_out;
+    unsigned long long *counters; // [0] frames ok, [1] frames failed, [2] payload bytes, [3] trellis steps
+    uint8_t *dbg_decoded;
+    uint32_t dbg_decoded_stride;
+    uint32_t *dbg_field;
+};
+
+cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s);
+
+cudaError_t upload_tables();
+
+} // namespace b200rx

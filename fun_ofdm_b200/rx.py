@@ -1,0 +1,215 @@
+"""ctypes binding of include/b200rx.h.  Mirrors the C ABI one to one; no decode logic lives here."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ST_OK, ST_HDR_PARITY, ST_HDR_RATE, ST_CRC_FAIL, ST_TRUNCATED, ST_TOO_LONG = range(6)
+RATE_INVALID = 255
+
+# fun::Rate -> (rate_field, cbps, dbps, bpsc)   reference src/rates.h:52-196
+RATE_PARAMS = {
+    0: (0xD, 48, 24, 1), 1: (0xE, 48, 32, 1), 2: (0xF, 48, 36, 1),
+    3: (0x5, 96, 48, 2), 4: (0x6, 96, 64, 2), 5: (0x7, 96, 72, 2),
+    6: (0x9, 192, 96, 4), 7: (0xA, 192, 128, 4), 8: (0xB, 192, 144, 4),
+    9: (0x1, 288, 192, 6), 10: (0x3, 288, 216, 6),
+}
+
+
+def num_symbols(rate, length):
+    """Data OFDM symbols of a frame (reference src/ppdu.cpp:38-40)."""
+    return -(-(16 + 8 * (length + 4) + 6) // RATE_PARAMS[rate][2])
+
+
+def window_samples(rate, length):
+    """Complex samples from the LTS1 tag to the end of the frame: 2 LTS + SIGNAL + data symbols."""
+    return 128 + 80 * (1 + num_symbols(rate, length))
+
+
+class B200RxError(RuntimeError):
+    pass
+
+
+class Limits(C.Structure):
+    _fields_ = [("max_frames", C.c_uint32), ("max_payload_bytes", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+
+
+class Debug(C.Structure):
+    _fields_ = [("equalized", C.c_void_p), ("eq_vectors", C.c_uint32),
+                ("decoded", C.c_void_p), ("decoded_stride", C.c_uint32),
+                ("header_field", C.c_void_p),
+                ("depunct", C.c_void_p), ("depunct_stride", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("frontend_ms", C.c_float), ("viterbi_ms", C.c_float), ("traceback_ms", C.c_float),
+                ("total_ms", C.c_float), ("trellis_steps", C.c_uint64), ("frames_ok", C.c_uint32),
+                ("frames_failed", C.c_uint32), ("payload_bytes", C.c_uint64)]
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200rx.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libb200rx.so and declare every prototype of include/b200rx.h.  Raises if it is missing:
+    the product has no other implementation of the path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise B200RxError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    L.b200rx_create.restype = C.c_int
+    L.b200rx_create.argtypes = [C.c_int, C.POINTER(Limits), C.POINTER(vp)]
+    L.b200rx_destroy.restype = C.c_int
+    L.b200rx_destroy.argtypes = [vp]
+    L.b200rx_last_error.restype = C.c_char_p
+    L.b200rx_last_error.argtypes = [vp]
+    L.b200rx_version.restype = C.c_char_p
+    L.b200rx_version.argtypes = []
+    L.b200rx_set_stream.restype = C.c_int
+    L.b200rx_set_stream.argtypes = [vp, vp]
+    L.b200rx_synchronize.restype = C.c_int
+    L.b200rx_synchronize.argtypes = [vp]
+    L.b200rx_host_alloc.restype = C.c_int
+    L.b200rx_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.b200rx_host_free.restype = C.c_int
+    L.b200rx_host_free.argtypes = [vp]
+    L.b200rx_decode_batch.restype = C.c_int
+    L.b200rx_decode_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp]
+    L.b200rx_decode_batch_dev.restype = C.c_int
+    L.b200rx_decode_batch_dev.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp, C.POINTER(Debug)]
+    L.b200rx_viterbi_batch_dev.restype = C.c_int
+    L.b200rx_viterbi_batch_dev.argtypes = [vp, vp, u64, vp, u32, u32, vp, u32]
+    L.b200rx_get_stats.restype = C.c_int
+    L.b200rx_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.b200rx_launch_count.restype = u64
+    L.b200rx_launch_count.argtypes = [vp]
+    L.b200rx_max_steps.restype = u32
+    L.b200rx_max_steps.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+class Receiver:
+    """One b200rx handle (one GPU).  Thin: every method is one C-ABI call."""
+
+    def __init__(self, device=0, max_frames=4096, max_payload_bytes=1500):
+        self.lib = load_library()
+        self.max_frames = int(max_frames)
+        self.max_payload_bytes = int(max_payload_bytes)
+        self.device = int(device)
+        lim = Limits(self.max_frames, self.max_payload_bytes, (C.c_uint32 * 6)())
+        h = C.c_void_p()
+        rc = self.lib.b200rx_create(self.device, C.byref(lim), C.byref(h))
+        if rc != 0:
+            raise B200RxError("b200rx_create failed (%d): %s" % (rc, self.lib.b200rx_last_error(None).decode()))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise B200RxError("%s failed (%d): %s" % (what, rc, self.lib.b200rx_last_error(self.h).decode()))
+
+    @property
+    def max_steps(self):
+        return int(self.lib.b200rx_max_steps(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.b200rx_launch_count(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.b200rx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or None)), "b200rx_set_stream")
+
+    def synchronize(self):
+        self._check(self.lib.b200rx_synchronize(self.h), "b200rx_synchronize")
+
+    def stats(self):
+        st = Stats()
+        self._check(self.lib.b200rx_get_stats(self.h, C.byref(st)), "b200rx_get_stats")
+        return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    # ---- host buffers (numpy) ----
+    def decode_batch(self, iq, lts1_index, avail, payload_stride=None):
+        """iq: complex128 or float64 (re, im interleaved) numpy array.  Returns
+        (payload[n, stride] u8, length[n] u16, rate[n] u8, status[n] u8)."""
+        iq = np.ascontiguousarray(iq)
+        if iq.dtype == np.complex128:
+            iq = iq.view(np.float64)
+        assert iq.dtype == np.float64
+        lts1 = np.ascontiguousarray(lts1_index, dtype=np.uint64)
+        av = np.ascontiguousarray(avail, dtype=np.uint32)
+        n = len(lts1)
+        stride = int(payload_stride or self.max_payload_bytes)
+        payload = np.zeros((n, stride), dtype=np.uint8)
+        length = np.zeros(n, dtype=np.uint16)
+        rate = np.zeros(n, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.uint8)
+        rc = self.lib.b200rx_decode_batch(self.h, iq.ctypes.data, iq.size // 2, lts1.ctypes.data, av.ctypes.data, n,
+                                          payload.ctypes.data, stride, length.ctypes.data, rate.ctypes.data,
+                                          status.ctypes.data)
+        self._check(rc, "b200rx_decode_batch")
+        return payload, length, rate, status
+
+    def decode_batch_ptr(self, iq_ptr, iq_samples, lts1_ptr, avail_ptr, n, payload_ptr, stride, len_ptr, rate_ptr,
+                         status_ptr):
+        """Host-buffer entry point on raw addresses (pinned buffers owned by the caller)."""
+        rc = self.lib.b200rx_decode_batch(self.h, iq_ptr, iq_samples, lts1_ptr, avail_ptr, n, payload_ptr, stride,
+                                          len_ptr, rate_ptr, status_ptr)
+        self._check(rc, "b200rx_decode_batch")
+
+    # ---- device buffers (torch tensors on this device) ----
+    def decode_batch_dev(self, iq, lts1_index, avail, payload, length, rate, status, debug=None):
+        """All arguments are torch CUDA tensors: iq float64 [2*samples] (or complex128), lts1_index int64/uint64
+        [n], avail int32 [n], payload uint8 [n, stride], length int16 [n], rate uint8 [n], status uint8 [n].
+        Asynchronous on the handle's stream."""
+        n = int(lts1_index.numel())
+        iq_samples = int(iq.numel() if iq.is_complex() else iq.numel() // 2)
+        dbg = None
+        if debug:
+            dbg = Debug()
+            if debug.get("equalized") is not None:
+                dbg.equalized = debug["equalized"].data_ptr()
+                dbg.eq_vectors = int(debug["equalized"].shape[1])
+            if debug.get("decoded") is not None:
+                dbg.decoded = debug["decoded"].data_ptr()
+                dbg.decoded_stride = int(debug["decoded"].shape[1])
+            if debug.get("header_field") is not None:
+                dbg.header_field = debug["header_field"].data_ptr()
+            if debug.get("depunct") is not None:
+                dbg.depunct = debug["depunct"].data_ptr()
+                dbg.depunct_stride = int(debug["depunct"].shape[1])
+        rc = self.lib.b200rx_decode_batch_dev(
+            self.h, _ptr(iq), iq_samples, _ptr(lts1_index), _ptr(avail), n,
+            _ptr(payload), int(payload.shape[1]) if payload is not None else 0,
+            _ptr(length), _ptr(rate), _ptr(status), C.byref(dbg) if dbg is not None else None)
+        self._check(rc, "b200rx_decode_batch_dev")
+
+    def viterbi_batch_dev(self, symbols, data_bits, max_data_bits, out):
+        """symbols uint8 [n, stride] depunctured soft symbols; data_bits int32 [n]; out uint8 [n, out_stride]."""
+        n = int(data_bits.numel())
+        rc = self.lib.b200rx_viterbi_batch_dev(self.h, _ptr(symbols), int(symbols.shape[1]), _ptr(data_bits),
+                                               int(max_data_bits), n, _ptr(out), int(out.shape[1]))
+        self._check(rc, "b200rx_viterbi_batch_dev")

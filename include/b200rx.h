@@ -1,0 +1,162 @@
+/* b200rx — C ABI of the B200-native batched 802.11a receive hot path.
+ *
+ * Drop-in boundary for bmorgan5/fun_ofdm's receiver path after timing_sync: the four blocks
+ *     fft_symbols -> channel_est -> phase_tracker -> frame_decoder
+ * (reference src/receiver_chain.cpp:33-36 creates them, :47-50 chains them, :106-126 drives them)
+ * are replaced by one batched call that takes already-synchronised frames (the samples from each
+ * frame's LTS1 tag onwards) and returns payload bytes, rate, length and a status per frame.
+ *
+ * Plain pointers and sizes only; no C++/torch types; never throws; never keeps a caller pointer
+ * after the call returns.  Every entry point returns 0 on success or a negative B200RX_E_* code;
+ * b200rx_last_error() gives the text.  There is NO CPU fallback: without a CUDA device of compute
+ * capability 10.x b200rx_create() fails with B200RX_E_CUDA.
+ *
+ * The library (fun_ofdm_b200/lib/libb200rx.so) is built by `python -c "import __graft_entry__ as g; g.build()"`
+ * or `make -C fun_ofdm_b200/csrc`.
+ */
+#ifndef B200RX_H
+#define B200RX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200RX_API __attribute__((visibility("default")))
+#else
+#define B200RX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes ---- */
+#define B200RX_OK 0
+#define B200RX_E_ARG (-1)    /* bad argument (NULL, zero size, exceeds the handle's limits) */
+#define B200RX_E_CUDA (-2)   /* a CUDA call failed; see b200rx_last_error() */
+#define B200RX_E_NOMEM (-3)  /* device or pinned-host allocation failed */
+#define B200RX_E_DEVICE (-4) /* no usable sm_100 device */
+
+/* ---- per-frame status byte ---- (the reference only drops such frames silently or with a stderr
+ * line: frame_decoder.cpp:78, ppdu.cpp:187-203, ppdu.cpp:274-279) */
+#define B200RX_ST_OK 0          /* header valid, CRC-32 matches: payload delivered */
+#define B200RX_ST_HDR_PARITY 1  /* SIGNAL parity check failed (ppdu.cpp:187-191) */
+#define B200RX_ST_HDR_RATE 2    /* rate field not in VALID_RATES (ppdu.cpp:197-203, rates.h:21) */
+#define B200RX_ST_CRC_FAIL 3    /* CRC-32 mismatch (ppdu.cpp:274-279) */
+#define B200RX_ST_TRUNCATED 4   /* fewer samples than 128 + 80*(1 + nsym) were supplied for the frame */
+#define B200RX_ST_TOO_LONG 5    /* decoded LENGTH exceeds the handle's max_payload_bytes */
+
+/* ---- fun::Rate enum values (reference src/rates.h:31-44), as written to rate_out ---- */
+#define B200RX_RATE_1_2_BPSK 0
+#define B200RX_RATE_2_3_BPSK 1
+#define B200RX_RATE_3_4_BPSK 2
+#define B200RX_RATE_1_2_QPSK 3
+#define B200RX_RATE_2_3_QPSK 4
+#define B200RX_RATE_3_4_QPSK 5
+#define B200RX_RATE_1_2_QAM16 6
+#define B200RX_RATE_2_3_QAM16 7
+#define B200RX_RATE_3_4_QAM16 8
+#define B200RX_RATE_2_3_QAM64 9
+#define B200RX_RATE_3_4_QAM64 10
+#define B200RX_RATE_INVALID 255
+
+typedef struct b200rx_handle b200rx_handle;
+
+/* Capacity of a handle.  Device scratch (branch metrics 4 B and survivor words 8 B per trellis
+ * step per frame) is sized from these once, at create time. */
+typedef struct {
+    uint32_t max_frames;        /* frames per decode call */
+    uint32_t max_payload_bytes; /* largest LENGTH to decode, <= 4095 (12-bit field, ppdu.cpp:195) */
+    uint32_t reserved[6];       /* zero */
+} b200rx_limits;
+
+/* Optional taps for parity tests (DEVICE pointers; any may be NULL).  Not a product feature. */
+typedef struct {
+    double *equalized;          /* [n_frames][eq_vectors][48][2]: phase_tracker output (SIGNAL first) */
+    uint32_t eq_vectors;        /* vectors reserved per frame */
+    uint8_t *decoded;           /* [n_frames][decoded_stride]: Viterbi output bytes before descrambling */
+    uint32_t decoded_stride;
+    uint32_t *header_field;     /* [n_frames]: 24-bit decoded SIGNAL field */
+    uint8_t *depunct;           /* [n_frames][depunct_stride]: depunctured soft symbols, 2 per trellis step */
+    uint32_t depunct_stride;
+} b200rx_debug;
+
+/* Device time of each stage of the most recent batch (CUDA events on the handle's stream). */
+typedef struct {
+    float frontend_ms;  /* CP strip + FFT + channel estimate + equalise + phase track + demap + branch metrics */
+    float viterbi_ms;   /* add-compare-select */
+    float traceback_ms; /* traceback + descramble + CRC-32 + payload write */
+    float total_ms;
+    uint64_t trellis_steps; /* sum over frames of nsym * dbps actually decoded */
+    uint32_t frames_ok;
+    uint32_t frames_failed;
+    uint64_t payload_bytes; /* of CRC-OK frames */
+} b200rx_stats;
+
+/* Lifetime.  One handle per GPU per host thread; a handle is not re-entrant. */
+B200RX_API int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out);
+B200RX_API int b200rx_destroy(b200rx_handle *h);
+B200RX_API const char *b200rx_last_error(const b200rx_handle *h); /* h may be NULL: last create() error */
+B200RX_API const char *b200rx_version(void);
+
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) instead of the handle's own.
+ * NULL restores the handle-owned stream. */
+B200RX_API int b200rx_set_stream(b200rx_handle *h, void *cuda_stream);
+B200RX_API int b200rx_synchronize(b200rx_handle *h);
+
+/* Pinned host memory for the host-buffer entry point (plain malloc'ed memory also works, slower). */
+B200RX_API int b200rx_host_alloc(void **ptr, size_t bytes);
+B200RX_API int b200rx_host_free(void *ptr);
+
+/* Replaces fft_symbols::work + channel_est::work + phase_tracker::work + frame_decoder::work
+ * (fft_symbols.cpp:33-80, channel_est.cpp:36-85, phase_tracker.cpp:70-105, frame_decoder.cpp:45-91,
+ * ppdu.cpp:168-295) for n_frames isolated frames.  HOST buffers; copies in, decodes, copies out,
+ * returns when the results are in the caller's arrays.
+ *
+ *   iq            interleaved (re, im) doubles == std::complex<double>[] (the `sample` members of the
+ *                 tagged_sample stream, tagged_vector.h:82-94); iq_samples complex samples in total
+ *   lts1_index[f] index into iq of the sample timing_sync tagged LTS1 for frame f (timing_sync.cpp:105);
+ *                 LTS2 is implied 64 samples later (timing_sync.cpp:106)
+ *   avail[f]      complex samples available to frame f from lts1_index[f] on
+ *   payload_out   [n_frames][payload_stride] bytes; frame f's payload (LENGTH bytes) starts at f*payload_stride
+ *   payload_len   [n_frames] decoded LENGTH (0 if the header failed)
+ *   rate_out      [n_frames] fun::Rate value or B200RX_RATE_INVALID
+ *   status        [n_frames] B200RX_ST_*
+ */
+B200RX_API int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
+                        const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
+                        uint8_t *payload_out, uint32_t payload_stride,
+                        uint16_t *payload_len, uint8_t *rate_out, uint8_t *status);
+
+/* Same contract with every array already in DEVICE memory; asynchronous on the handle's stream
+ * (call b200rx_synchronize or sync the stream yourself).  dbg may be NULL. */
+B200RX_API int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_samples,
+                            const uint64_t *lts1_index_dev, const uint32_t *avail_dev, uint32_t n_frames,
+                            uint8_t *payload_out_dev, uint32_t payload_stride,
+                            uint16_t *payload_len_dev, uint8_t *rate_out_dev, uint8_t *status_dev,
+                            const b200rx_debug *dbg);
+
+/* Replaces viterbi::conv_decode (viterbi.cpp:31-37: alloc/init/FULL_SPIRAL/chainback) for a batch.
+ * DEVICE buffers.  symbols: depunctured soft symbols (0..255, erasure 127), frame f at
+ * symbols_dev + f*symbols_stride, 2*(data_bits[f] + 6) bytes each.  out: frame f's decoded bytes at
+ * out_dev + f*out_stride, ceil(data_bits[f] / 8) bytes, MSB first.  data_bits[f] + 6 must be even
+ * (it is for every rate: viterbi.cpp:209 processes two steps per pass) and <= the handle's capacity. */
+B200RX_API int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint64_t symbols_stride,
+                             const uint32_t *data_bits_dev, uint32_t max_data_bits, uint32_t n_frames,
+                             uint8_t *out_dev, uint32_t out_stride);
+
+/* Counters and per-stage device times of the most recent decode call on this handle
+ * (synchronises the handle's stream). */
+B200RX_API int b200rx_get_stats(b200rx_handle *h, b200rx_stats *out);
+
+/* Number of kernels launched by this handle since creation (for gpu_launches accounting). */
+B200RX_API uint64_t b200rx_launch_count(const b200rx_handle *h);
+
+/* Trellis capacity (steps per frame) the handle was sized for. */
+B200RX_API uint32_t b200rx_max_steps(const b200rx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* B200RX_H */

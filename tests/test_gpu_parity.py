@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA path through the C ABI against the checker (reference compiled under
+oracle/_ref, or the C port when that is absent) on identical samples.
+
+Bars: payload bytes, LENGTH, rate, status, decoded (pre-descramble) bytes, header field and the
+depunctured soft symbols are BIT-EXACT; equalised constellation points within 1e-9 absolute
+(north star: <= 1e-4 relative to symbol energy; fp64 on both sides gives ~1e-14).
+"""
+import numpy as np
+import pytest
+
+from tests.util import checker_decode, make_corpus
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+EQ_TOL = 1e-9
+
+
+def _checker():
+    from oracle import bind
+    return bind.ref() if bind.have_ref() else bind.port()
+
+
+def gpu_decode(rx, corpus, taps=True):
+    dev = torch.device("cuda:0")
+    n = len(corpus["lts1"])
+    iq = torch.from_numpy(corpus["iq"].view(np.float64)).to(dev)
+    lts1 = torch.from_numpy(corpus["lts1"]).to(dev)
+    avail = torch.from_numpy(corpus["avail"]).to(dev)
+    stride = rx.max_payload_bytes
+    payload = torch.zeros((n, max(stride, 1)), dtype=torch.uint8, device=dev)
+    length = torch.zeros(n, dtype=torch.int16, device=dev)
+    rate = torch.zeros(n, dtype=torch.uint8, device=dev)
+    status = torch.full((n,), 99, dtype=torch.uint8, device=dev)
+    dbg = None
+    if taps:
+        max_vec = int(max((a - 128) // 80 for a in corpus["avail"])) + 1
+        dbg = dict(
+            equalized=torch.zeros((n, max_vec, 48, 2), dtype=torch.float64, device=dev),
+            decoded=torch.zeros((n, rx.max_steps // 8 + 8), dtype=torch.uint8, device=dev),
+            header_field=torch.zeros(n, dtype=torch.int32, device=dev),
+            depunct=torch.zeros((n, 2 * rx.max_steps), dtype=torch.uint8, device=dev),
+        )
+    rx.decode_batch_dev(iq, lts1, avail, payload, length, rate, status, dbg)
+    rx.synchronize()
+    out = dict(payload=payload.cpu().numpy(), length=length.cpu().numpy().astype(np.uint16).astype(int),
+               rate=rate.cpu().numpy(), status=status.cpu().numpy())
+    if taps:
+        out.update({k: v.cpu().numpy() for k, v in dbg.items()})
+    return out
+
+
+def compare(corpus, got, want, taps=True):
+    n = len(want)
+    n_ok = 0
+    for f in range(n):
+        w = want[f]
+        tag = "frame %d (rate %s len %s)" % (f, corpus["rates"][f], corpus["lengths"][f])
+        if taps:
+            assert int(got["header_field"][f]) == w.hdr_field, tag
+        if not w.hdr_ok:
+            assert got["status"][f] in (1, 2), tag
+            assert got["status"][f] == (1 if w.hdr_parity else 2), tag
+            continue
+        assert got["rate"][f] == w.rate and got["length"][f] == w.length, tag
+        if w.n_vectors < 1 + w.nsym:
+            assert got["status"][f] == 4, tag
+            continue
+        assert got["status"][f] == (0 if w.crc_ok else 3), tag
+        if taps:
+            nv = 1 + w.nsym
+            eq = got["equalized"][f, :nv].view(np.complex128)[..., 0]
+            err = np.abs(eq - w.eq[:nv]).max()
+            assert err < EQ_TOL, (tag, err)
+            assert np.array_equal(got["depunct"][f, : len(w.depunct)], w.depunct), tag
+            assert np.array_equal(got["decoded"][f, : len(w.decoded)], w.decoded), tag
+        if w.crc_ok:
+            n_ok += 1
+            assert bytes(got["payload"][f, : w.length]) == bytes(w.payload), tag
+        else:
+            # payload bytes of a failing frame are still the reference's descrambled bytes
+            assert bytes(got["payload"][f, : w.length]) == bytes(w.descrambled[2: 2 + w.length]), tag
+    return n_ok
+
+
+@pytest.mark.parametrize("rate", list(range(11)))
+def test_all_rates_clean_and_noisy(ref, rx_factory, rate):
+    """Config 3: every rate (8 standard + 3 non-standard 2/3), clean and at an SNR where many frames fail."""
+    rng = np.random.default_rng(100 + rate)
+    rx = rx_factory(64, 1500)
+    fail_snr = [2, 4, 6, 5, 7, 9, 11, 13, 15, 19, 21][rate]
+    total_ok = 0
+    for snr in (None, 30, fail_snr):
+        n = 6 if rate < 3 else 12
+        lengths = [1500] + list(rng.integers(0, 1500, n - 1))
+        corpus = make_corpus(ref, rng, [rate] * n, lengths, snr_db=snr)
+        want = checker_decode(ref, corpus)
+        got = gpu_decode(rx, corpus)
+        ok = compare(corpus, got, want)
+        total_ok += ok
+        if snr is None and rate in (0, 3, 6, 8, 9, 10):  # rates with no noiseless self-failures
+            assert ok == n
+    assert total_ok > 0
+
+
+def test_mixed_batch_truncated_and_garbage(ref, rx_factory):
+    """Ragged input: mixed rates and lengths, truncated frames, pure noise, zero-length payload."""
+    rng = np.random.default_rng(7)
+    rx = rx_factory(64, 1500)
+    rates = [10, 0, 5, 8, 3, 9, 10, 6, 2, 10]
+    lengths = [0, 1, 37, 1500, 700, 1499, 64, 255, 100, 1000]
+    corpus = make_corpus(ref, rng, rates, lengths, snr_db=28)
+    corpus["avail"][2] -= 200      # truncated data part
+    corpus["avail"][5] = 150       # not even a SIGNAL symbol
+    corpus["avail"][7] = 208       # SIGNAL only
+    # a window of pure noise
+    noise_at = len(corpus["iq"])
+    corpus["iq"] = np.concatenate([corpus["iq"], 0.05 * (rng.standard_normal(3000) + 1j * rng.standard_normal(3000))])
+    corpus["lts1"] = np.append(corpus["lts1"], noise_at)
+    corpus["avail"] = np.append(corpus["avail"], 3000).astype(np.int32)
+    corpus["rates"].append(-1)
+    corpus["lengths"].append(-1)
+    want = checker_decode(ref, corpus)
+    got = gpu_decode(rx, corpus)
+    compare(corpus, got, want)
+    assert got["status"][5] == 4 and got["status"][7] == 4 and got["status"][2] == 4
+
+
+def test_host_buffer_entry_point_matches_device_entry_point(ref, rx_factory):
+    rng = np.random.default_rng(11)
+    rx = rx_factory(64, 1500)
+    corpus = make_corpus(ref, rng, [10, 8, 0, 4], [1500, 300, 20, 999], snr_db=26)
+    got_dev = gpu_decode(rx, corpus, taps=False)
+    payload, length, rate, status = rx.decode_batch(corpus["iq"], corpus["lts1"], corpus["avail"])
+    assert np.array_equal(status, got_dev["status"])
+    assert np.array_equal(length.astype(int), got_dev["length"])
+    assert np.array_equal(rate, got_dev["rate"])
+    assert np.array_equal(payload, got_dev["payload"])
+    want = checker_decode(ref, corpus)
+    for f, w in enumerate(want):
+        if w.crc_ok:
+            assert bytes(payload[f, : w.length]) == bytes(w.payload)
+
+
+def test_multipath(ref, rx_factory):
+    """Config 5 flavour: <= 8-tap multipath + AWGN, genie tags; verdicts and bytes identical."""
+    rng = np.random.default_rng(23)
+    rx = rx_factory(64, 4095)
+    rates = list(rng.choice([0, 2, 3, 5, 6, 8, 9, 10], 24))
+    lengths = list(rng.integers(64, 4096, 24))
+    corpus = make_corpus(ref, rng, rates, lengths, snr_db=30, multipath_taps=4)
+    want = checker_decode(ref, corpus)
+    got = gpu_decode(rx, corpus)
+    compare(corpus, got, want)
+
+
+def test_viterbi_only_entry_point(ref, rx_factory):
+    """Config 4: conv_encode -> puncture -> noise -> depuncture -> b200rx_viterbi_batch_dev vs viterbi::conv_decode."""
+    rng = np.random.default_rng(5)
+    rx = rx_factory(64, 1500)
+    dev = torch.device("cuda:0")
+    cases = []
+    for rate, sigma in [(0, 0), (0, 60), (1, 40), (2, 10), (10, 60), (10, 90), (9, 90), (8, 120)]:
+        for nbits in (18, 90, 2042, 12090):
+            steps = nbits + 6
+            if rate in (2, 5, 8, 10):
+                steps -= steps % 6          # whole puncture periods (3 steps)
+            elif rate in (1, 4, 7, 9):
+                steps -= steps % 2
+            nb = steps - 6
+            data = rng.integers(0, 256, (nb + 6 + 7) // 8 + 1, dtype=np.uint8)
+            coded = ref.conv_encode(data, nb)
+            tx = ref.puncture(coded, rate).astype(np.float64) * 255.0
+            rxs = np.clip(np.rint(tx + sigma * rng.standard_normal(len(tx))), 0, 255).astype(np.uint8)
+            dep = ref.depuncture(rxs, rate)
+            assert len(dep) == 2 * steps
+            cases.append((nb, dep, ref.conv_decode(dep, nb)))
+    n = len(cases)
+    stride = 2 * rx.max_steps
+    sym = np.zeros((n, stride), np.uint8)
+    for i, (nb, dep, _) in enumerate(cases):
+        sym[i, : len(dep)] = dep
+    bits = np.array([c[0] for c in cases], np.int32)
+    out = torch.zeros((n, rx.max_steps // 8 + 8), dtype=torch.uint8, device=dev)
+    rx.viterbi_batch_dev(torch.from_numpy(sym).to(dev), torch.from_numpy(bits).to(dev), int(bits.max()), out)
+    rx.synchronize()
+    out = out.cpu().numpy()
+    for i, (nb, _, want) in enumerate(cases):
+        assert np.array_equal(out[i, : len(want)], want), (i, nb)
