@@ -6,9 +6,10 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
 import fun_ofdm_b200 as fo
 from oracle import bind
-from tests.util import make_corpus
+from ofdm_testutil import make_corpus
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 ref = bind.ref()

@@ -8,7 +8,7 @@ depunctured soft symbols are BIT-EXACT; equalised constellation points within 1e
 import numpy as np
 import pytest
 
-from tests.util import checker_decode, make_corpus
+from ofdm_testutil import checker_decode, make_corpus
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -56,6 +56,9 @@ def compare(corpus, got, want, taps=True):
     for f in range(n):
         w = want[f]
         tag = "frame %d (rate %s len %s)" % (f, corpus["rates"][f], corpus["lengths"][f])
+        if w.n_vectors < 1:  # not even a SIGNAL symbol in the window
+            assert got["status"][f] == 4, tag
+            continue
         if taps:
             assert int(got["header_field"][f]) == w.hdr_field, tag
         if not w.hdr_ok:
