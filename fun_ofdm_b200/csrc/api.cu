@@ -10,6 +10,7 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 using namespace b200rx;
 
@@ -23,6 +24,9 @@ struct b200rx_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
+    // optional per-call stage timing over many calls (b200rx_profile_begin/read)
+    std::vector<cudaEvent_t> ring; // 4 events per slot
+    uint32_t ring_slots = 0, ring_used = 0;
 
     // device scratch
     FrameDesc *desc = nullptr;
@@ -52,6 +56,13 @@ int fail(b200rx_handle *h, int code, const char *what, cudaError_t ce = cudaSucc
     else snprintf(buf, sizeof(buf), "%s", what);
     if (h) h->error = buf; else g_create_error = buf;
     return code;
+}
+
+// events of the current call: a ring slot while profiling, the handle's single set otherwise
+inline cudaEvent_t *call_events(b200rx_handle *h)
+{
+    if (h->ring_slots && h->ring_used < h->ring_slots) return &h->ring[4 * (size_t)(h->ring_used++)];
+    return h->ev;
 }
 
 #define CU(h, call)                                                         \
@@ -192,6 +203,7 @@ int b200rx_destroy(b200rx_handle *h)
     cudaFree(h->d_iq); cudaFree(h->d_lts1); cudaFree(h->d_avail); cudaFree(h->d_payload);
     cudaFree(h->d_len); cudaFree(h->d_rate); cudaFree(h->d_status);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return B200RX_OK;
@@ -226,6 +238,13 @@ int b200rx_host_free(void *ptr)
     return cudaFreeHost(ptr) == cudaSuccess ? B200RX_OK : B200RX_E_CUDA;
 }
 
+int b200rx_device_counters(b200rx_handle *h, void **dev_ptr)
+{
+    if (!h || !dev_ptr) return B200RX_E_ARG;
+    *dev_ptr = h->counters;
+    return B200RX_OK;
+}
+
 uint64_t b200rx_launch_count(const b200rx_handle *h) { return h ? h->launches : 0; }
 uint32_t b200rx_max_steps(const b200rx_handle *h) { return h ? h->max_steps : 0; }
 
@@ -244,7 +263,8 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
     cudaStream_t s = h->stream;
 
     CU(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), s));
-    CU(h, cudaEventRecord(h->ev[0], s));
+    cudaEvent_t *ev = call_events(h);
+    CU(h, cudaEventRecord(ev[0], s));
 
     FrontendArgs fa{};
     fa.iq = reinterpret_cast<const double2 *>(iq_dev);
@@ -264,9 +284,9 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
         fa.dbg_depunct_stride = dbg->depunct_stride;
     }
     CU(h, launch_frontend(fa, s));
-    CU(h, cudaEventRecord(h->ev[1], s));
+    CU(h, cudaEventRecord(ev[1], s));
     CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, h->max_steps, n_frames, s));
-    CU(h, cudaEventRecord(h->ev[2], s));
+    CU(h, cudaEventRecord(ev[2], s));
 
     TracebackArgs ta{};
     ta.desc = h->desc;
@@ -286,8 +306,8 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
         ta.dbg_field = dbg->header_field;
     }
     CU(h, launch_traceback(ta, s));
-    CU(h, cudaEventRecord(h->ev[3], s));
-    h->ev_valid = true;
+    CU(h, cudaEventRecord(ev[3], s));
+    if (ev == h->ev) h->ev_valid = true;
     h->launches += 3;
     return B200RX_OK;
 }
@@ -365,6 +385,37 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
     CU(h, cudaEventRecord(h->ev[3], s));
     h->ev_valid = true;
     h->launches += 3;
+    return B200RX_OK;
+}
+
+int b200rx_profile_begin(b200rx_handle *h, uint32_t slots)
+{
+    if (!h) return B200RX_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
+    h->ring.assign(4 * (size_t)slots, nullptr);
+    for (size_t i = 0; i < h->ring.size(); i++) CU(h, cudaEventCreate(&h->ring[i]));
+    h->ring_slots = slots;
+    h->ring_used = 0;
+    return B200RX_OK;
+}
+
+int b200rx_profile_read(b200rx_handle *h, uint32_t *calls, float *frontend_ms, float *viterbi_ms, float *traceback_ms)
+{
+    if (!h || !calls || !frontend_ms || !viterbi_ms || !traceback_ms) return B200RX_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *calls = h->ring_used;
+    *frontend_ms = *viterbi_ms = *traceback_ms = 0.f;
+    for (uint32_t i = 0; i < h->ring_used; i++) {
+        cudaEvent_t *e = &h->ring[4 * (size_t)i];
+        float a, b, c;
+        CU(h, cudaEventElapsedTime(&a, e[0], e[1]));
+        CU(h, cudaEventElapsedTime(&b, e[1], e[2]));
+        CU(h, cudaEventElapsedTime(&c, e[2], e[3]));
+        *frontend_ms += a; *viterbi_ms += b; *traceback_ms += c;
+    }
+    h->ring_slots = 0; // profiling ends with the read
     return B200RX_OK;
 }
 

@@ -90,6 +90,13 @@ def load_library():
     L.b200rx_viterbi_batch_dev.argtypes = [vp, vp, u64, vp, u32, u32, vp, u32]
     L.b200rx_get_stats.restype = C.c_int
     L.b200rx_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.b200rx_profile_begin.restype = C.c_int
+    L.b200rx_profile_begin.argtypes = [vp, u32]
+    L.b200rx_profile_read.restype = C.c_int
+    L.b200rx_profile_read.argtypes = [vp, C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float)]
+    L.b200rx_device_counters.restype = C.c_int
+    L.b200rx_device_counters.argtypes = [vp, C.POINTER(vp)]
     L.b200rx_launch_count.restype = u64
     L.b200rx_launch_count.argtypes = [vp]
     L.b200rx_max_steps.restype = u32
@@ -150,6 +157,27 @@ class Receiver:
         st = Stats()
         self._check(self.lib.b200rx_get_stats(self.h, C.byref(st)), "b200rx_get_stats")
         return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    def device_counters(self):
+        """torch int64[4] view of the handle's device counters {ok, failed, payload bytes, trellis steps}."""
+        import torch
+        p = C.c_void_p()
+        self._check(self.lib.b200rx_device_counters(self.h, C.byref(p)), "b200rx_device_counters")
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (4,), "typestr": "<i8", "data": (p.value, False), "version": 2}
+
+        return torch.as_tensor(_Arr(), device=torch.device("cuda", self.device))
+
+    def profile_begin(self, slots):
+        self._check(self.lib.b200rx_profile_begin(self.h, int(slots)), "b200rx_profile_begin")
+
+    def profile_read(self):
+        """-> (calls, frontend_ms_sum, viterbi_ms_sum, traceback_ms_sum)"""
+        n, a, b, c = C.c_uint32(), C.c_float(), C.c_float(), C.c_float()
+        self._check(self.lib.b200rx_profile_read(self.h, C.byref(n), C.byref(a), C.byref(b), C.byref(c)),
+                    "b200rx_profile_read")
+        return n.value, a.value, b.value, c.value
 
     # ---- host buffers (numpy) ----
     def decode_batch(self, iq, lts1_index, avail, payload_stride=None):

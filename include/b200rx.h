@@ -149,6 +149,19 @@ B200RX_API int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols
  * (synchronises the handle's stream). */
 B200RX_API int b200rx_get_stats(b200rx_handle *h, b200rx_stats *out);
 
+/* Per-stage device times summed over the next `slots` decode calls (one CUDA-event quadruple per call,
+ * recorded on the handle's stream, so the kernels are timed in place inside whatever region the
+ * caller is timing).  b200rx_profile_read synchronises the stream, returns the number of calls
+ * recorded and the three sums in milliseconds, and ends the profiling window. */
+B200RX_API int b200rx_profile_begin(b200rx_handle *h, uint32_t slots);
+B200RX_API int b200rx_profile_read(b200rx_handle *h, uint32_t *calls, float *frontend_ms, float *viterbi_ms,
+                                   float *traceback_ms);
+
+/* DEVICE address of the handle's four 64-bit counters of the most recent decode call
+ * {frames ok, frames failed, payload bytes of ok frames, trellis steps}: lets a multi-GPU driver
+ * reduce them with one collective (NCCL all-reduce) without a host round trip. */
+B200RX_API int b200rx_device_counters(b200rx_handle *h, void **dev_ptr);
+
 /* Number of kernels launched by this handle since creation (for gpu_launches accounting). */
 B200RX_API uint64_t b200rx_launch_count(const b200rx_handle *h);
 
