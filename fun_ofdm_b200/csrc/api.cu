@@ -31,7 +31,7 @@ struct b200rx_handle {
     // device scratch
     FrameDesc *desc = nullptr;
     uint32_t *bm = nullptr;
-    uint2 *dec = nullptr;
+    uint32_t *dec = nullptr; // survivor words: 2 per trellis step per frame
     unsigned long long *counters = nullptr; // 4 words
 
     // staging for the host-buffer entry point (grow-only)
@@ -176,7 +176,7 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
     A((void **)&h->desc, nf * sizeof(FrameDesc));
     A((void **)&h->bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
-    A((void **)&h->dec, nf * (size_t)h->max_steps * sizeof(uint2));
+    A((void **)&h->dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
     A((void **)&h->counters, 4 * sizeof(unsigned long long));
     A((void **)&h->d_lts1, nf * sizeof(uint64_t));
     A((void **)&h->d_avail, nf * sizeof(uint32_t));
@@ -285,13 +285,13 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
     }
     CU(h, launch_frontend(fa, s));
     CU(h, cudaEventRecord(ev[1], s));
-    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, h->max_steps, n_frames, s));
+    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, 2 * h->max_steps, n_frames, s));
     CU(h, cudaEventRecord(ev[2], s));
 
     TracebackArgs ta{};
     ta.desc = h->desc;
     ta.dec = h->dec;
-    ta.dec_stride = h->max_steps;
+    ta.dec_stride = 2 * h->max_steps;
     ta.n_frames = n_frames;
     ta.raw_mode = 0;
     ta.payload = payload_out_dev;
@@ -370,12 +370,12 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
     CU(h, launch_bm_from_symbols(symbols_dev, symbols_stride, data_bits_dev, max_data_bits, n_frames, h->desc, h->bm,
                                  h->max_steps, h->max_steps, s));
     CU(h, cudaEventRecord(h->ev[1], s));
-    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, h->max_steps, n_frames, s));
+    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, 2 * h->max_steps, n_frames, s));
     CU(h, cudaEventRecord(h->ev[2], s));
     TracebackArgs ta{};
     ta.desc = h->desc;
     ta.dec = h->dec;
-    ta.dec_stride = h->max_steps;
+    ta.dec_stride = 2 * h->max_steps;
     ta.n_frames = n_frames;
     ta.raw_mode = 1;
     ta.payload = out_dev;

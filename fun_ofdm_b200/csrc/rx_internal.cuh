@@ -51,7 +51,8 @@ __host__ __device__ __forceinline__ uint32_t num_symbols(int rate, uint32_t leng
     return (16u + 8u * (length + 4u) + 6u + dbps - 1u) / dbps;
 }
 
-// Largest trellis (steps) any rate needs for a payload of max_len bytes, rounded up to 32.
+// Largest trellis (steps) any rate needs for a payload of max_len bytes, rounded up to a multiple of 96
+// (the ACS kernel works in blocks of 24 steps, metric words are moved 4 at a time).
 inline uint32_t max_steps_for(uint32_t max_len)
 {
     uint32_t m = 0;
@@ -59,7 +60,7 @@ inline uint32_t max_steps_for(uint32_t max_len)
         uint32_t s = num_symbols(r, max_len) * rate_row(r).dbps;
         if (s > m) m = s;
     }
-    return (m + 31u) & ~31u;
+    return ((m + 95u) / 96u) * 96u;
 }
 
 // ---- per-frame descriptor written by the front end, read by the Viterbi and traceback kernels ----
@@ -94,15 +95,6 @@ __host__ __device__ __forceinline__ uint32_t branch_class(uint32_t j)
     return (b0 << 1) | b1;
 }
 
-// ---- survivor (decision) storage ----
-// One uint2 per trellis step: .x bit l = decision of new state 2l, .y bit l = decision of new state 2l+1
-// (decision 1 = survivor came from predecessor j+32, viterbi.cpp:256-273).
-__device__ __forceinline__ uint32_t decision_bit(const uint2 *dec, uint32_t t, uint32_t state)
-{
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(dec + t) + (state & 1u);
-    return (__ldg(w) >> (state >> 1)) & 1u;
-}
-
 // ---- launchers (each returns the cudaError_t of the launch) ----
 struct FrontendArgs {
     const double2 *iq;
@@ -128,13 +120,13 @@ cudaError_t launch_bm_from_symbols(const uint8_t *symbols, uint64_t symbols_stri
                                    uint32_t max_data_bits, uint32_t n_frames, FrameDesc *desc, uint32_t *bm,
                                    uint32_t bm_stride, uint32_t max_steps, cudaStream_t s);
 
-cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride, uint2 *dec,
-                               uint32_t dec_stride, uint32_t n_frames, cudaStream_t s);
+cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride, uint32_t *dec,
+                               uint32_t dec_stride_words, uint32_t n_frames, cudaStream_t s);
 
 struct TracebackArgs {
     FrameDesc *desc;
-    const uint2 *dec;
-    uint32_t dec_stride;
+    const uint32_t *dec;     // survivor words, layout of viterbi_acs2.cuh
+    uint32_t dec_stride;     // uint32 words per frame
     uint32_t n_frames;
     int raw_mode;            // 1: Viterbi-only entry point — write decoded bytes, no descramble/CRC
     uint8_t *payload;

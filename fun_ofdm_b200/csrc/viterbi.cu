@@ -8,6 +8,7 @@
 //   payload extraction      (src/ppdu.cpp:284-289)                                     -> traceback_kernel
 #include "rx_internal.cuh"
 #include "viterbi_core.cuh"
+#include "viterbi_acs2.cuh"
 
 namespace b200rx {
 
@@ -44,49 +45,88 @@ __global__ void bm_from_symbols_kernel(const uint8_t *symbols, uint64_t symbols_
 }
 
 // ------------------------------------------------------------------------------------------------
-// ACS: one warp per frame (see viterbi_core.cuh for the lane layout).  Per 32 steps: one coalesced
-// 128 B load of metric words, one coalesced 256 B store of survivor words.
+// ACS, second generation (viterbi_acs2.cuh): 8 lanes per frame, 4 frames per warp, metrics in place.
+// Per 24 steps and frame: one 96 B read of metric words (staged through shared memory, double
+// buffered, prefetched one block ahead) and three 64 B survivor stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int ACS_WARPS = 4;
+constexpr int ACS2_WARPS = 2;
 
-__global__ void __launch_bounds__(ACS_WARPS * 32) viterbi_acs_kernel(const FrameDesc *desc, const uint32_t *bm,
-                                                                      uint32_t bm_stride, uint2 *dec,
-                                                                      uint32_t dec_stride, uint32_t n_frames)
+template <int PH>
+__device__ __forceinline__ void acs2_one(uint32_t (&R)[ACS2_NR], uint32_t &acc0, uint32_t &acc1, uint32_t w,
+                                         const Acs2Lane &L, int glane, int group)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t frame = blockIdx.x * ACS_WARPS + (threadIdx.x >> 5);
-    if (frame >= n_frames) return;
-    const uint32_t n_steps = desc[frame].n_steps;
-    if (n_steps == 0) return;
-    const uint32_t *w_in = bm + (size_t)frame * bm_stride;
-    uint2 *d_out = dec + (size_t)frame * dec_stride;
+    uint32_t D[ACS2_NR];
+    acs2_step<PH>(R, D, w, L);
+    // bytes 1 and 3 of each raw decision word are 0/1: gather 4 of them, shift into the 8-step history
+    acc0 = acc0 * 2u + __byte_perm(D[0], D[1], 0x7531u);
+    acc1 = acc1 * 2u + __byte_perm(D[2], D[3], 0x7531u);
+    acs2_renorm(R, glane, group);
+}
 
-    const AcsLane ln = acs_lane_init(lane);
-    uint32_t R = acs_initial_metrics(lane);
-    uint32_t cur = ((uint32_t)lane < n_steps) ? __ldg(w_in + lane) : 0u;
-    for (uint32_t t0 = 0; t0 < n_steps; t0 += 32) {
-        const uint32_t tn = t0 + 32 + lane;
-        const uint32_t nxt = (tn < n_steps) ? __ldg(w_in + tn) : 0u;
-        uint32_t my_e = 0, my_o = 0;
-        const int cnt = min(32u, n_steps - t0);
-        if (cnt == 32) {
+__global__ void __launch_bounds__(ACS2_WARPS * 32) viterbi_acs2_kernel(const FrameDesc *desc, const uint32_t *bm,
+                                                                        uint32_t bm_stride, uint32_t *dec,
+                                                                        uint32_t dec_stride_words, uint32_t n_frames)
+{
+    static_assert(ACS2_NR == 4, "decision packing below assumes 4 registers per lane");
+    __shared__ __align__(16) uint32_t s_w[ACS2_WARPS][2][ACS2_FPW][ACS2_BLK];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = lane >> ACS2_LB, glane = lane & (ACS2_T - 1);
+    const uint32_t frame0 = (blockIdx.x * ACS2_WARPS + warp) * ACS2_FPW;
+    if (frame0 >= n_frames) return;
+    const uint32_t frame = min(frame0 + group, n_frames - 1); // surplus groups shadow the last frame (no stores)
+    const bool live = frame0 + group < n_frames;
+    const uint32_t n_steps = live ? desc[frame].n_steps : 0u;
+    const uint32_t my_blocks = (n_steps + ACS2_BLK - 1) / ACS2_BLK;
+    const uint32_t n_blocks = __reduce_max_sync(0xFFFFFFFFu, my_blocks);
+    if (n_blocks == 0) return;
+
+    const uint32_t *w_in = bm + (size_t)frame * bm_stride;
+    uint32_t *d_out = dec + (size_t)frame * dec_stride_words;
+
+    Acs2Lane L;
+    acs2_lane_init(L, glane);
+    uint32_t R[ACS2_NR];
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                uint32_t de, dod;
-                const uint32_t Y = acs_step(R, __shfl_sync(VIT_FULL, cur, i), ln, lane, de, dod);
-                if (lane == i) { my_e = de; my_o = dod; }
-                R = acs_next(Y, ln);
+    for (int i = 0; i < ACS2_NR; i++) R[i] = 0x003F003Fu;
+    if (glane == 0) R[0] = 0x0000003Fu; // state 0 (high half of register 0) starts at 0 (viterbi.cpp:71-78)
+
+    // lanes 0..5 of each group move the group's 24 metric words (6 x 16 B) per block
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    if (glane < 6) pre = __ldg(reinterpret_cast<const uint4 *>(w_in) + glane);
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        uint32_t *sw = &s_w[warp][b & 1][group][0];
+        if (glane < 6) reinterpret_cast<uint4 *>(sw)[glane] = pre;
+        __syncwarp();
+        if (glane < 6 && b + 1 < n_blocks && (b + 1) < my_blocks + 0u)
+            pre = __ldg(reinterpret_cast<const uint4 *>(w_in + (size_t)(b + 1) * ACS2_BLK) + glane);
+        uint32_t *d_blk = d_out + (size_t)b * 3 * ACS2_WORDS_PER_8 + glane * 2;
+        const bool store = b < my_blocks;
+#pragma unroll
+        for (int o = 0; o < 3; o++) {
+            const uint4 wa = reinterpret_cast<const uint4 *>(sw)[2 * o];
+            const uint4 wb = reinterpret_cast<const uint4 *>(sw)[2 * o + 1];
+            uint32_t acc0 = 0, acc1 = 0;
+            // 8 steps; phase = (8 * o + i) % 6
+            if (o == 0) {
+                acs2_one<0>(R, acc0, acc1, wa.x, L, glane, group); acs2_one<1>(R, acc0, acc1, wa.y, L, glane, group);
+                acs2_one<2>(R, acc0, acc1, wa.z, L, glane, group); acs2_one<3>(R, acc0, acc1, wa.w, L, glane, group);
+                acs2_one<4>(R, acc0, acc1, wb.x, L, glane, group); acs2_one<5>(R, acc0, acc1, wb.y, L, glane, group);
+                acs2_one<0>(R, acc0, acc1, wb.z, L, glane, group); acs2_one<1>(R, acc0, acc1, wb.w, L, glane, group);
+            } else if (o == 1) {
+                acs2_one<2>(R, acc0, acc1, wa.x, L, glane, group); acs2_one<3>(R, acc0, acc1, wa.y, L, glane, group);
+                acs2_one<4>(R, acc0, acc1, wa.z, L, glane, group); acs2_one<5>(R, acc0, acc1, wa.w, L, glane, group);
+                acs2_one<0>(R, acc0, acc1, wb.x, L, glane, group); acs2_one<1>(R, acc0, acc1, wb.y, L, glane, group);
+                acs2_one<2>(R, acc0, acc1, wb.z, L, glane, group); acs2_one<3>(R, acc0, acc1, wb.w, L, glane, group);
+            } else {
+                acs2_one<4>(R, acc0, acc1, wa.x, L, glane, group); acs2_one<5>(R, acc0, acc1, wa.y, L, glane, group);
+                acs2_one<0>(R, acc0, acc1, wa.z, L, glane, group); acs2_one<1>(R, acc0, acc1, wa.w, L, glane, group);
+                acs2_one<2>(R, acc0, acc1, wb.x, L, glane, group); acs2_one<3>(R, acc0, acc1, wb.y, L, glane, group);
+                acs2_one<4>(R, acc0, acc1, wb.z, L, glane, group); acs2_one<5>(R, acc0, acc1, wb.w, L, glane, group);
             }
-        } else {
-            for (int i = 0; i < cnt; i++) {
-                uint32_t de, dod;
-                const uint32_t Y = acs_step(R, __shfl_sync(VIT_FULL, cur, i), ln, lane, de, dod);
-                if (lane == i) { my_e = de; my_o = dod; }
-                R = acs_next(Y, ln);
-            }
+            if (store) *reinterpret_cast<uint2 *>(d_blk + o * ACS2_WORDS_PER_8) = make_uint2(acc0, acc1);
         }
-        if (lane < cnt) d_out[t0 + lane] = make_uint2(my_e, my_o);
-        cur = nxt;
+        __syncwarp();
     }
 }
 
@@ -104,13 +144,13 @@ constexpr int TB_TILE = 96;  // decoded bits per tile (multiple of 8)
 constexpr int TB_PRE = 96;   // speculative pre-roll
 constexpr int TB_MAX_BYTES = 4224; // >= (8*(4095+6)+6+215)/8
 
-__device__ __forceinline__ uint32_t walk_tile(const uint2 *dec, uint32_t e, int n_from, int n_to, int out_below,
+__device__ __forceinline__ uint32_t walk_tile(const uint32_t *dec, uint32_t e, int n_from, int n_to, int out_below,
                                               uint8_t *bytes, int entry_at, uint32_t *entry_state)
 {
     // processes decoded-bit indices n = n_from-1 ... n_to (descending); survivor word of bit n is step n+6
     for (int n = n_from - 1; n >= n_to; n--) {
         if (n == entry_at) *entry_state = e >> 2;
-        const uint32_t k = decision_bit(dec, (uint32_t)n + 6u, e >> 2);
+        const uint32_t k = acs2_decision_bit(dec, (uint32_t)n + 6u, e >> 2);
         e = (e >> 1) | (k << 7);
         if (n < out_below && (n & 7) == 0) bytes[n >> 3] = (uint8_t)e;
     }
@@ -143,7 +183,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
     if (!a.raw_mode)
         for (int i = tid; i < 1024; i += TB_THREADS) (&s_crc[0][0])[i] = (&c_crc_tab[0][0])[i];
 
-    const uint2 *dec = a.dec + (size_t)frame * a.dec_stride;
+    const uint32_t *dec = a.dec + (size_t)frame * a.dec_stride;
     const int nbytes = (nbits + 7) >> 3;
     const int ntiles = (nbits + TB_TILE - 1) / TB_TILE;
 
@@ -250,12 +290,13 @@ cudaError_t launch_bm_from_symbols(const uint8_t *symbols, uint64_t symbols_stri
     return cudaGetLastError();
 }
 
-cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride, uint2 *dec,
-                               uint32_t dec_stride, uint32_t n_frames, cudaStream_t s)
+cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride, uint32_t *dec,
+                               uint32_t dec_stride_words, uint32_t n_frames, cudaStream_t s)
 {
     if (n_frames == 0) return cudaSuccess;
-    viterbi_acs_kernel<<<(n_frames + ACS_WARPS - 1) / ACS_WARPS, ACS_WARPS * 32, 0, s>>>(desc, bm, bm_stride, dec,
-                                                                                           dec_stride, n_frames);
+    const uint32_t per_cta = ACS2_WARPS * ACS2_FPW;
+    viterbi_acs2_kernel<<<(n_frames + per_cta - 1) / per_cta, ACS2_WARPS * 32, 0, s>>>(desc, bm, bm_stride, dec,
+                                                                                         dec_stride_words, n_frames);
     return cudaGetLastError();
 }
 
