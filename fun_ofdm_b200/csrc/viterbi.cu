@@ -65,7 +65,8 @@ __device__ __forceinline__ void acs2_one(uint32_t (&R)[ACS2_NR], uint32_t &acc0,
 
 __global__ void __launch_bounds__(ACS2_WARPS * 32) viterbi_acs2_kernel(const FrameDesc *desc, const uint32_t *bm,
                                                                         uint32_t bm_stride, uint32_t *dec,
-                                                                        uint32_t dec_stride_words, uint32_t n_frames)
+                                                                        uint32_t dec_stride_words, uint32_t n_frames,
+                                                                        uint32_t neg1)
 {
     static_assert(ACS2_NR == 4, "decision packing below assumes 4 registers per lane");
     __shared__ __align__(16) uint32_t s_w[ACS2_WARPS][2][ACS2_FPW][ACS2_BLK];
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(ACS2_WARPS * 32) viterbi_acs2_kernel(const Fra
     uint32_t *d_out = dec + (size_t)frame * dec_stride_words;
 
     Acs2Lane L;
-    acs2_lane_init(L, glane);
+    acs2_lane_init(L, glane, neg1);
     uint32_t R[ACS2_NR];
 #pragma unroll
     for (int i = 0; i < ACS2_NR; i++) R[i] = 0x003F003Fu;
@@ -296,7 +297,7 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
     if (n_frames == 0) return cudaSuccess;
     const uint32_t per_cta = ACS2_WARPS * ACS2_FPW;
     viterbi_acs2_kernel<<<(n_frames + per_cta - 1) / per_cta, ACS2_WARPS * 32, 0, s>>>(desc, bm, bm_stride, dec,
-                                                                                         dec_stride_words, n_frames);
+                                                                                         dec_stride_words, n_frames, 0xFFFFFFFFu);
     return cudaGetLastError();
 }
 

@@ -69,14 +69,26 @@ __device__ __forceinline__ uint32_t acs2_prmt(uint32_t a, uint32_t b, uint32_t s
     return d;
 }
 
+// a * b + c forced onto the FMA pipe (IMAD); with b = -1 this is c - a.  The ALU pipe is the bottleneck
+// of this kernel (ncu: 61 % busy vs 9 % for the FMA pipe), so every op that can move does.
+__device__ __forceinline__ uint32_t acs2_fma(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 struct Acs2Lane {
     uint32_t sel[6][ACS2_NR]; // PRMT selector (hi class, lo class) per phase and register
     uint32_t selB[ACS2_NR];   // second selector of the half-bit phase
     int sgn[ACS2_LB], nsgn[ACS2_LB];
+    uint32_t neg1, one;       // 0xFFFFFFFF and 1 derived from a kernel argument so that ptxas keeps the IMADs
 };
 
-__device__ __forceinline__ void acs2_lane_init(Acs2Lane &L, int glane)
+__device__ __forceinline__ void acs2_lane_init(Acs2Lane &L, int glane, uint32_t neg1)
 {
+    L.neg1 = neg1;
+    L.one = 0u - neg1;
 #pragma unroll
     for (int r = 0; r < 6; r++) {
 #pragma unroll
@@ -109,7 +121,6 @@ constexpr uint32_t ACS2_C = 0x01000100u;
 template <int PH>
 __device__ __forceinline__ void acs2_step(uint32_t (&R)[ACS2_NR], uint32_t (&D)[ACS2_NR], uint32_t w, const Acs2Lane &L)
 {
-    const uint32_t wc = w ^ 0x3F3F3F3Fu; // 63 - m per byte (psubusb 63, m: viterbi.cpp:246-248)
     constexpr int axis = 5 - PH;         // position bit separating the butterfly partners
     if constexpr (axis >= 6 - ACS2_LB) {
         // ---- partners in another lane ----
@@ -119,7 +130,7 @@ __device__ __forceinline__ void acs2_step(uint32_t (&R)[ACS2_NR], uint32_t (&D)[
 #pragma unroll
         for (int i = 0; i < ACS2_NR; i++) {
             const uint32_t M = acs2_prmt(w, w, L.sel[PH][i]);
-            const uint32_t Mi = acs2_prmt(wc, wc, L.sel[PH][i]);
+            const uint32_t Mi = acs2_fma(M, L.neg1, 0x003F003Fu);           // 63 - m per half, on the FMA pipe
             const uint32_t G = __viaddmin_u16x2(R[i], Mi, ACS2_CAP);            // my candidate for the partner's new state
             const uint32_t S = __shfl_xor_sync(0xFFFFFFFFu, G, 1 << lbit);      // partner's candidate for mine
             const uint32_t V = __viaddmin_u16x2(R[i], M, ACS2_CAP);             // my own candidate
@@ -134,18 +145,19 @@ __device__ __forceinline__ void acs2_step(uint32_t (&R)[ACS2_NR], uint32_t (&D)[
             if ((a >> q) & 1) continue;
             const int b = a | (1 << q);
             const uint32_t M = acs2_prmt(w, w, L.sel[PH][a]);
-            const uint32_t Mi = acs2_prmt(wc, wc, L.sel[PH][a]);
+            const uint32_t Mi = acs2_fma(M, L.neg1, 0x003F003Fu);
             const uint32_t B = __viaddmin_u16x2(R[b], Mi, ACS2_CAP); // via j+32 -> new state 2j
             const uint32_t E = __viaddmin_u16x2(R[b], M, ACS2_CAP);  // via j+32 -> new state 2j+1
             const uint32_t Ya = __viaddmin_u16x2(R[a], M, B);        // min(X[j] + m, B); ties keep B's value
             const uint32_t Yb = __viaddmin_u16x2(R[a], Mi, E);
-            D[a] = Ya + ACS2_C - B;
-            D[b] = Yb + ACS2_C - E;
+            D[a] = acs2_fma(Ya, L.one, acs2_fma(B, L.neg1, ACS2_C));
+            D[b] = acs2_fma(Yb, L.one, acs2_fma(E, L.neg1, ACS2_C));
             R[a] = Ya;
             R[b] = Yb;
         }
     } else {
         // ---- partners are the two halves of one register: high = state j, low = state j+32 ----
+        const uint32_t wc = w ^ 0x3F3F3F3Fu; // 63 - m per byte (psubusb 63, m: viterbi.cpp:246-248)
 #pragma unroll
         for (int i = 0; i < ACS2_NR; i++) {
             const uint32_t W = __byte_perm(R[i], R[i], 0x3232u); // (X[j], X[j])
@@ -154,7 +166,7 @@ __device__ __forceinline__ void acs2_step(uint32_t (&R)[ACS2_NR], uint32_t (&D)[
             const uint32_t MB = acs2_prmt(w, wc, L.selB[i]);    // (63-m, m)
             const uint32_t V = __viaddmin_u16x2(Z, MB, ACS2_CAP); // via j+32: (-> 2j, -> 2j+1)
             const uint32_t Y = __viaddmin_u16x2(W, MA, V);
-            D[i] = Y + ACS2_C - V;
+            D[i] = acs2_fma(Y, L.one, acs2_fma(V, L.neg1, ACS2_C));
             R[i] = Y;
         }
     }
@@ -165,8 +177,8 @@ __device__ __forceinline__ void acs2_step(uint32_t (&R)[ACS2_NR], uint32_t (&D)[
 __device__ __forceinline__ void acs2_renorm(uint32_t (&R)[ACS2_NR], int glane, int group)
 {
     const bool hot = (glane == 0) && (R[0] > 0x00D2FFFFu);
-    const uint32_t any = __ballot_sync(0xFFFFFFFFu, hot);
-    if (any) {
+    if (__any_sync(0xFFFFFFFFu, hot)) {
+        const uint32_t any = __ballot_sync(0xFFFFFFFFu, hot);
         uint32_t m = R[0];
 #pragma unroll
         for (int i = 1; i < ACS2_NR; i++) m = __vminu2(m, R[i]);
