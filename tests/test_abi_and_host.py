@@ -1,0 +1,130 @@
+"""CPU tests: the C-ABI libraries load and export every symbol include/*.h declares; without a GPU the
+product fails loudly (no CPU fallback); host-side frame generator against the golden vectors / reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.dirname(os.path.abspath(__file__))
+FRAMES = np.load(os.path.join(HERE, "golden", "frames.npz"))
+KAT = np.load(os.path.join(HERE, "golden", "stage_kat.npz"))
+META = FRAMES["meta"]
+
+
+def _declared(header, macro):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(macro + r"[^;(]*?\b(b200[rt]x_\w+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    import fun_ofdm_b200 as fo
+    from fun_ofdm_b200 import tx
+    if not (os.path.exists(fo.lib_path()) and os.path.exists(tx.host_lib_path())):
+        g.build()
+    return fo, tx
+
+
+def test_rx_library_exports_every_declared_symbol(built):
+    fo, _ = built
+    names = _declared("b200rx.h", "B200RX_API")
+    assert len(names) >= 17, names
+    lib = C.CDLL(fo.lib_path())
+    for n in names:
+        assert hasattr(lib, n), n
+    assert b"sm_100a" in fo.load_library().b200rx_version()
+
+
+def test_tx_library_exports_every_declared_symbol(built):
+    _, tx = built
+    names = _declared("b200tx.h", "B200TX_API")
+    assert len(names) >= 6, names
+    lib = C.CDLL(tx.host_lib_path())
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device handle creation must fail with a clear error, never fall back."""
+    import torch
+    fo, _ = built
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fo.B200RxError) as e:
+        fo.Receiver(0, 16, 100)
+    assert "no CPU path" in str(e.value)
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "fun_ofdm_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "oracle" not in text.replace("oracle/_ref", "").replace("oracle/", "") or f == "__init__.py", f
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_frame_generator_matches_golden(built):
+    _, tx = built
+    for k in range(len(META)):
+        rate = int(META[k][0])
+        payload = FRAMES["tx_payload_%d" % k]
+        pts = tx.ppdu_encode(payload.tobytes(), rate)
+        assert np.array_equal(pts, FRAMES["tx_points_%d" % k]), k  # constellation points: exact
+        f = tx.build_frame(payload.tobytes(), rate)
+        want = FRAMES["tx_frame_%d" % k]
+        assert len(f) == len(want)
+        # preamble: the reference's table is printed to 12 digits; data symbols: IFFT rounding only
+        assert np.abs(f[:320] - want[:320]).max() < 1e-12
+        assert np.abs(f[320:] - want[320:]).max() < 1e-15 * 64
+
+
+def test_tables_match_reference_tables(built):
+    _, tx = built
+    assert np.abs(tx.preamble() - KAT["preamble"]).max() < 1e-12
+    lts = KAT["lts_freq"]
+    assert np.all(lts.imag == 0)
+    nz = sum(1 << i for i, v in enumerate(lts.real) if v != 0)
+    neg = sum(1 << i for i, v in enumerate(lts.real) if v < 0)
+    text = open(os.path.join(ROOT, "fun_ofdm_b200", "csrc", "frontend.cu")).read()
+    assert "0x%016Xull" % nz in text.replace("0x0", "0x0") or hex(nz)[2:].upper() in text.upper()
+    assert hex(neg)[2:].upper() in text.upper()
+
+
+def test_frame_generator_matches_reference_on_random_payloads(built, ref):
+    _, tx = built
+    rng = np.random.default_rng(4)
+    for rate in range(11):
+        for length in (0, 1, 333, 4095):
+            pl = rng.integers(0, 256, length, dtype=np.uint8).tobytes()
+            assert np.array_equal(tx.ppdu_encode(pl, rate), ref.ppdu_encode(pl, rate))
+            assert np.abs(tx.build_frame(pl, rate) - ref.build_frame(pl, rate)).max() < 1e-12
+
+
+def test_corpus_is_deterministic_and_decodes_with_the_port(built, port):
+    _, tx = built
+    rng = np.random.default_rng(8)
+    payloads = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (10, 200, 64, 0, 150)]
+    rates = [0, 10, 5, 8, 3]
+    a = tx.build_corpus(payloads, rates, snr_db=30, lead_in=16, seed=5, threads=1)
+    b = tx.build_corpus(payloads, rates, snr_db=30, lead_in=16, seed=5, threads=4)
+    assert np.array_equal(a["iq"], b["iq"])
+    c = tx.build_corpus(payloads, rates, snr_db=30, lead_in=16, seed=6, threads=4)
+    assert not np.array_equal(a["iq"], c["iq"])
+    for f in range(len(rates)):
+        off, n = int(a["lts1"][f]), int(a["avail"][f])
+        d = port.decode_frame(a["iq"][off: off + n])
+        assert d.hdr_ok and d.crc_ok and bytes(d.payload) == payloads[f]
+    # multipath: still decodable at QPSK with the 8 spare CP samples
+    m = tx.build_corpus(payloads[:3], [3, 3, 3], snr_db=30, multipath_taps=4, seed=9, threads=2)
+    ok = 0
+    for f in range(3):
+        off, n = int(m["lts1"][f]), int(m["avail"][f])
+        d = port.decode_frame(m["iq"][off: off + n])
+        ok += int(d.hdr_ok and d.crc_ok)
+    assert ok >= 2

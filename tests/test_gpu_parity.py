@@ -190,3 +190,82 @@ def test_viterbi_only_entry_point(ref, rx_factory):
     out = out.cpu().numpy()
     for i, (nb, _, want) in enumerate(cases):
         assert np.array_equal(out[i, : len(want)], want), (i, nb)
+
+
+def test_golden_frames_on_gpu(rx_factory):
+    """Committed fixtures generated from the compiled reference (tests/golden/make_golden.py): does not
+    need oracle/_ref at run time."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames.npz"))
+    meta = g["meta"]
+    wins = [g["window_%d" % k] for k in range(len(meta))]
+    corpus = dict(iq=np.concatenate(wins),
+                  lts1=np.cumsum([0] + [len(w) for w in wins[:-1]]).astype(np.int64),
+                  avail=np.array([len(w) for w in wins], np.int32))
+    rx = rx_factory(64, 1500)
+    got = gpu_decode(rx, corpus)
+    for k in range(len(meta)):
+        rate, length, snr, hdr_ok, field, par, rate_valid, drate, dlen, nsym, crc_ok, nvec = (int(x) for x in meta[k])
+        assert int(got["header_field"][k]) == field
+        if not hdr_ok:
+            assert got["status"][k] == (1 if par else 2)
+            continue
+        assert (got["rate"][k], got["length"][k]) == (drate, dlen)
+        assert got["status"][k] == (0 if crc_ok else 3)
+        eq = got["equalized"][k, : 1 + nsym].view(np.complex128)[..., 0]
+        assert np.abs(eq - g["eq_%d" % k][: 1 + nsym]).max() < EQ_TOL
+        dep = g["depunct_%d" % k]
+        assert np.array_equal(got["depunct"][k, : len(dep)], dep)
+        dec = g["decoded_%d" % k]
+        assert np.array_equal(got["decoded"][k, : len(dec)], dec)
+        if crc_ok:
+            assert bytes(got["payload"][k, :dlen]) == bytes(g["payload_%d" % k])
+
+
+def test_config2_full_batch_properties_and_sampled_parity(rx_factory):
+    """BASELINE config 2 at full size (4096 x 1500 B, 54 Mbps, 25 dB) from the product's generator:
+    size-independent properties on every frame (a CRC-OK frame carries exactly the transmitted payload;
+    decoding twice gives identical output), and bit-exact parity with the checker on a 192-frame sample."""
+    from fun_ofdm_b200 import tx
+    rng = np.random.default_rng(0xB200)
+    n = 4096
+    payloads = rng.integers(0, 256, (n, 1500), dtype=np.uint8)
+    corpus = tx.build_corpus(payloads, np.full(n, 10, np.uint8), snr_db=25.0, seed=0xB200)
+    c = dict(iq=corpus["iq"], lts1=corpus["lts1"].astype(np.int64), avail=corpus["avail"].astype(np.int32))
+    rx = rx_factory(n, 1500)
+    a = gpu_decode(rx, c, taps=False)
+    b = gpu_decode(rx, c, taps=False)
+    for key in ("payload", "length", "rate", "status"):
+        assert np.array_equal(a[key], b[key]), key
+    ok = a["status"] == 0
+    assert ok.sum() > 0.9 * n
+    assert set(np.unique(a["status"])) <= {0, 3}
+    assert np.all(a["length"] == 1500) and np.all(a["rate"] == 10)
+    assert np.array_equal(a["payload"][ok], payloads[ok])
+    checker = _checker()
+    idx = np.concatenate([np.arange(96), np.nonzero(~ok)[0][:32], rng.integers(0, n, 64)])
+    for f in idx:
+        off, m = int(c["lts1"][f]), int(c["avail"][f])
+        w = checker.decode_frame(c["iq"][off: off + m])
+        assert (a["status"][f] == 0) == w.crc_ok, f
+        want = w.payload if w.crc_ok else w.descrambled[2: 2 + w.length]
+        assert bytes(a["payload"][f, : w.length]) == bytes(want), f
+
+
+def test_worst_case_length(rx_factory):
+    """Longest frames the 12-bit LENGTH field allows (4095 B): 32 832 trellis steps at BPSK 1/2."""
+    from fun_ofdm_b200 import tx
+    rng = np.random.default_rng(3)
+    rates = [0, 10, 2, 9]
+    payloads = [rng.integers(0, 256, 4095, dtype=np.uint8).tobytes() for _ in rates]
+    corpus = tx.build_corpus(payloads, rates, snr_db=30.0, seed=1)
+    c = dict(iq=corpus["iq"], lts1=corpus["lts1"].astype(np.int64), avail=corpus["avail"].astype(np.int32),
+             rates=rates, lengths=[4095] * 4)
+    rx = rx_factory(8, 4095)
+    got = gpu_decode(rx, c)
+    want = checker_decode(_checker(), c)
+    assert compare(c, got, want) >= 2
+    # a handle sized for short payloads must refuse them, not overflow
+    small = rx_factory(8, 100)
+    g2 = gpu_decode(small, c, taps=False)
+    assert np.all(g2["status"] == 5)
