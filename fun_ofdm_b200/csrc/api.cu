@@ -353,6 +353,48 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
     return B200RX_OK;
 }
 
+int b200rx_decode_headers(b200rx_handle *h, const double *iq, uint64_t iq_samples, const uint64_t *lts1_index,
+                          const uint32_t *avail, uint32_t n_frames, uint16_t *payload_len, uint8_t *rate_out,
+                          uint8_t *status)
+{
+    if (!h) return B200RX_E_ARG;
+    if (!iq || !lts1_index || !avail || !status) return fail(h, B200RX_E_ARG, "b200rx_decode_headers: null argument");
+    if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_headers: n_frames exceeds max_frames");
+    if (n_frames == 0) return B200RX_OK;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t iq_bytes = (size_t)iq_samples * 2 * sizeof(double);
+    if (iq_bytes > h->d_iq_cap) {
+        if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_decode_headers: sample staging", e);
+        h->d_iq_cap = iq_bytes;
+    }
+    CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    FrontendArgs fa{};
+    fa.iq = reinterpret_cast<const double2 *>(h->d_iq);
+    fa.iq_samples = iq_samples;
+    fa.lts1 = h->d_lts1;
+    fa.avail = h->d_avail;
+    fa.n_frames = n_frames;
+    fa.desc = h->desc;
+    fa.bm = h->bm;
+    fa.bm_stride = h->max_steps;
+    fa.max_steps = h->max_steps;
+    fa.max_len = h->limits.max_payload_bytes;
+    fa.header_only = 1;
+    CU(h, launch_frontend(fa, s));
+    CU(h, launch_export_headers(h->desc, n_frames, h->d_len, h->d_rate, h->d_status, s));
+    h->launches += 2;
+    if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+    if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, n_frames, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(status, h->d_status, n_frames, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    return B200RX_OK;
+}
+
 int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint64_t symbols_stride,
                              const uint32_t *data_bits_dev, uint32_t max_data_bits, uint32_t n_frames,
                              uint8_t *out_dev, uint32_t out_stride)

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
                 s_desc.rate = (uint8_t)rate;
                 s_desc.length = (uint16_t)len;
                 if (len > a.max_len || steps > a.max_steps) s_desc.status = B200RX_ST_TOO_LONG;
-                else if ((uint64_t)avail < 128ull + 80ull * (1ull + nsym)) s_desc.status = B200RX_ST_TRUNCATED;
+                else if (!a.header_only && (uint64_t)avail < 128ull + 80ull * (1ull + nsym)) s_desc.status = B200RX_ST_TRUNCATED;
                 else {
                     s_desc.status = B200RX_ST_OK;
                     s_desc.n_steps = steps;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     __syncthreads();
     const FrameDesc d = s_desc;
     if (tid == 0) a.desc[frame] = d;
-    if (d.status != B200RX_ST_OK) return;
+    if (d.status != B200RX_ST_OK || a.header_only) return;
 
     // ---- data symbols ----
     const RateRow rr = rate_row(d.rate);

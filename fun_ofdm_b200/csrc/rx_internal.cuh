@@ -107,6 +107,7 @@ struct FrontendArgs {
     uint32_t bm_stride;      // words per frame (>= max_steps, multiple of 32)
     uint32_t max_steps;
     uint32_t max_len;
+    int header_only;         // 1: stop after the SIGNAL symbol (descriptor only, no branch metrics)
     // taps (may be null)
     double2 *dbg_eq;
     uint32_t dbg_eq_vectors;
@@ -141,6 +142,9 @@ struct TracebackArgs {
 };
 
 cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s);
+
+cudaError_t launch_export_headers(const FrameDesc *desc, uint32_t n, uint16_t *len, uint8_t *rate, uint8_t *status,
+                                  cudaStream_t s);
 
 cudaError_t upload_tables();
 

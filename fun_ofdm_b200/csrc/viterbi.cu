@@ -301,6 +301,25 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
     return cudaGetLastError();
 }
 
+// Header-only decode: copy (rate, length, status) out of the descriptors the front end wrote.
+__global__ void export_headers_kernel(const FrameDesc *desc, uint32_t n, uint16_t *len, uint8_t *rate, uint8_t *status)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const FrameDesc d = desc[f];
+    if (len) len[f] = d.length;
+    if (rate) rate[f] = d.rate;
+    if (status) status[f] = d.status;
+}
+
+cudaError_t launch_export_headers(const FrameDesc *desc, uint32_t n, uint16_t *len, uint8_t *rate, uint8_t *status,
+                                  cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    export_headers_kernel<<<(n + 127) / 128, 128, 0, s>>>(desc, n, len, rate, status);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s)
 {
     if (a.n_frames == 0) return cudaSuccess;

@@ -136,6 +136,14 @@ B200RX_API int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, u
                             uint16_t *payload_len_dev, uint8_t *rate_out_dev, uint8_t *status_dev,
                             const b200rx_debug *dbg);
 
+/* Replaces ppdu::decode_header (ppdu.cpp:168-218) for n_frames frames: only the two LTS symbols and the
+ * SIGNAL symbol are read (208 samples from lts1_index[f]); gives the streaming adapter the frame length
+ * before the frame has fully arrived.  HOST buffers, synchronous.  status: B200RX_ST_OK (header valid; the
+ * frame needs 128 + 80 * (1 + nsym) samples), HDR_PARITY, HDR_RATE, TOO_LONG, or TRUNCATED (< 208 samples). */
+B200RX_API int b200rx_decode_headers(b200rx_handle *h, const double *iq, uint64_t iq_samples,
+                                     const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
+                                     uint16_t *payload_len, uint8_t *rate_out, uint8_t *status);
+
 /* Replaces viterbi::conv_decode (viterbi.cpp:31-37: alloc/init/FULL_SPIRAL/chainback) for a batch.
  * DEVICE buffers.  symbols: depunctured soft symbols (0..255, erasure 127), frame f at
  * symbols_dev + f*symbols_stride, 2*(data_bits[f] + 6) bytes each.  out: frame f's decoded bytes at

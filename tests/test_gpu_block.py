@@ -1,0 +1,103 @@
+"""GPU: fun::b200_rx (the C++ block that replaces fft_symbols..frame_decoder) against the reference's own
+four blocks on the same tagged_sample stream, chunk by chunk like receiver_chain::process_samples."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Block:
+    def __init__(self, max_frames=64, max_payload=4095):
+        self.lib = C.CDLL(os.path.join(ROOT, "fun_ofdm_b200", "lib", "libb200host.so"))
+        self.lib.b200host_rx_block_new.restype = C.c_void_p
+        self.lib.b200host_rx_block_new.argtypes = [C.c_int, C.c_uint, C.c_uint]
+        self.lib.b200host_rx_block_work.restype = C.c_int
+        self.lib.b200host_rx_block_work.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p,
+                                                    C.c_int, C.c_void_p, C.c_int]
+        self.lib.b200host_rx_block_delete.argtypes = [C.c_void_p]
+        self.lib.b200host_rx_block_counters.argtypes = [C.c_void_p, C.c_void_p]
+        self.h = self.lib.b200host_rx_block_new(0, max_frames, max_payload)
+        assert self.h, "b200_rx block could not be created (no GPU?)"
+
+    def work(self, samples, tags, flush=False, max_out=512, stride=4095):
+        iq = np.ascontiguousarray(samples, dtype=np.complex128).view(np.float64)
+        tags = np.ascontiguousarray(tags, dtype=np.uint8)
+        payload = np.zeros((max_out, stride), np.uint8)
+        length = np.zeros(max_out, np.int32)
+        n = self.lib.b200host_rx_block_work(self.h, iq.ctypes.data, tags.ctypes.data, len(tags), int(flush),
+                                            payload.ctypes.data, stride, length.ctypes.data, max_out)
+        return [bytes(payload[i, : length[i]]) for i in range(min(n, max_out))]
+
+    def counters(self):
+        c = np.zeros(5, np.uint64)
+        self.lib.b200host_rx_block_counters(self.h, c.ctypes.data)
+        return dict(zip(["seen", "headers_bad", "ok", "crc_fail", "abandoned"], (int(x) for x in c)))
+
+    def close(self):
+        self.lib.b200host_rx_block_delete(self.h)
+
+
+def _stream(ref, rng, rates, lengths, snr_db, gap=600):
+    chunks, payloads = [np.zeros(400, complex)], []
+    for rate, length in zip(rates, lengths):
+        pl = rng.integers(0, 256, length, dtype=np.uint8).tobytes()
+        f = ref.build_frame(pl, rate)
+        payloads.append(pl)
+        chunks += [f, np.zeros(gap, complex)]
+    chunks.append(np.zeros(8192, complex))
+    x = np.concatenate(chunks)
+    if snr_db is not None:
+        p = 0.0127  # mean |x|^2 of a frame body
+        sig = np.sqrt(p / 10 ** (snr_db / 10.0) / 2.0)
+        x = x + sig * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))
+    return x, payloads
+
+
+@pytest.mark.parametrize("snr", [None, 25])
+def test_block_matches_reference_blocks_on_synced_stream(ref, snr):
+    rng = np.random.default_rng(17 if snr is None else 18)
+    rates = [10, 8, 0, 5, 10, 3, 9, 6, 10, 2, 10, 10]
+    lengths = [1500, 300, 40, 700, 64, 1000, 1499, 255, 0, 120, 1500, 333]
+    x, payloads = _stream(ref, rng, rates, lengths, snr)
+    samples, tags = ref.sync(x, chunk=4096)          # reference frame_detector + timing_sync (the boundary producer)
+    assert (tags == 4).sum() >= len(rates) - 1        # LTS1 tags
+    want = ref.hotpath_stream(samples, tags, chunk=4096)
+    blk = Block()
+    got = []
+    for s in range(0, len(tags), 4096):
+        got += blk.work(samples[s: s + 4096], tags[s: s + 4096])
+    got += blk.work(np.zeros(1, complex), np.zeros(1, np.uint8), flush=True)
+    c = blk.counters()
+    blk.close()
+    assert got == want, (len(got), len(want), c)
+    assert len(got) >= len(rates) - 2
+    if snr is None:
+        assert got == [p for p in payloads if p in got]
+
+
+def test_block_genie_tags_and_frame_cut_short(ref):
+    """Genie tags (LTS1 at frame start + 184); a frame interrupted by the next LTS1 is abandoned, like the
+    reference (whose decoder restarts on the new valid SIGNAL, frame_decoder.cpp:86)."""
+    rng = np.random.default_rng(3)
+    f1 = ref.build_frame(rng.integers(0, 256, 800, dtype=np.uint8).tobytes(), 10)
+    pl2 = rng.integers(0, 256, 90, dtype=np.uint8).tobytes()
+    f2 = ref.build_frame(pl2, 6)
+    x = np.concatenate([f1[: len(f1) // 2], f2, np.zeros(500, complex)])
+    tags = np.zeros(len(x), np.uint8)
+    tags[184] = 4
+    tags[184 + 64] = 5
+    tags[len(f1) // 2 + 184] = 4
+    tags[len(f1) // 2 + 184 + 64] = 5
+    want = ref.hotpath_stream(x, tags, chunk=1000)
+    blk = Block()
+    got = []
+    for s in range(0, len(x), 1000):
+        got += blk.work(x[s: s + 1000], tags[s: s + 1000])
+    c = blk.counters()
+    blk.close()
+    assert got == want == [pl2]
+    assert c["abandoned"] == 1 and c["ok"] == 1
