@@ -32,7 +32,7 @@ struct b200rx_handle {
     FrameDesc *desc = nullptr;
     uint32_t *bm = nullptr;
     uint32_t *dec = nullptr; // survivor words: 2 per trellis step per frame
-    unsigned long long *counters = nullptr; // 4 words
+    unsigned long long *counters = nullptr; // 8 words (5 used)
 
     // staging for the host-buffer entry point (grow-only)
     double *d_iq = nullptr; size_t d_iq_cap = 0;
@@ -79,7 +79,7 @@ bool g_tables_uploaded[64] = {false};
 namespace b200rx {
 // defined next to the kernels that own the __constant__ symbols
 cudaError_t upload_frontend_tables(const double2 *tw, const int8_t *pol);
-cudaError_t upload_viterbi_tables(const uint32_t *crc, const uint8_t *scr);
+cudaError_t upload_viterbi_tables(const uint32_t *crc, const uint8_t *scr, const uint32_t *xpow);
 }
 
 cudaError_t b200rx::upload_tables()
@@ -130,7 +130,25 @@ cudaError_t b200rx::upload_tables()
         scr[x] = (uint8_t)fb;
         state = ((state << 1) & 0x7E) | fb;
     }
-    return upload_viterbi_tables(&crc[0][0], scr);
+    // CRC combine factors x^(8 * L * 2^lvl) mod P (reflected representation, bit 31 = x^0), for the
+    // warp-parallel CRC of the traceback kernel
+    auto multmodp = [](uint32_t a, uint32_t b) {
+        uint32_t p = 0;
+        for (int i = 31; i >= 0; i--) {
+            if ((a >> i) & 1u) p ^= b;
+            b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+        }
+        return p;
+    };
+    static uint32_t xpow[5][132];
+    const uint32_t x8 = 1u << 23; // x^8
+    uint32_t cur = 1u << 31;      // x^0
+    for (int L = 0; L < 132; L++) {
+        uint32_t f = cur;
+        for (int lvl = 0; lvl < 5; lvl++) { xpow[lvl][L] = f; f = multmodp(f, f); }
+        cur = multmodp(cur, x8);
+    }
+    return upload_viterbi_tables(&crc[0][0], scr, &xpow[0][0]);
 }
 
 extern "C" {
@@ -177,7 +195,7 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     A((void **)&h->desc, nf * sizeof(FrameDesc));
     A((void **)&h->bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
     A((void **)&h->dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
-    A((void **)&h->counters, 4 * sizeof(unsigned long long));
+    A((void **)&h->counters, 8 * sizeof(unsigned long long));
     A((void **)&h->d_lts1, nf * sizeof(uint64_t));
     A((void **)&h->d_avail, nf * sizeof(uint32_t));
     A((void **)&h->d_len, nf * sizeof(uint16_t));
@@ -262,7 +280,7 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
 
-    CU(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), s));
+    CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     cudaEvent_t *ev = call_events(h);
     CU(h, cudaEventRecord(ev[0], s));
 
@@ -407,7 +425,7 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
     if (n_frames == 0) return B200RX_OK;
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    CU(h, cudaMemsetAsync(h->counters, 0, 4 * sizeof(unsigned long long), s));
+    CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     CU(h, cudaEventRecord(h->ev[0], s));
     CU(h, launch_bm_from_symbols(symbols_dev, symbols_stride, data_bits_dev, max_data_bits, n_frames, h->desc, h->bm,
                                  h->max_steps, h->max_steps, s));
@@ -472,8 +490,9 @@ int b200rx_get_stats(b200rx_handle *h, b200rx_stats *out)
     CU(h, cudaEventElapsedTime(&out->viterbi_ms, h->ev[1], h->ev[2]));
     CU(h, cudaEventElapsedTime(&out->traceback_ms, h->ev[2], h->ev[3]));
     CU(h, cudaEventElapsedTime(&out->total_ms, h->ev[0], h->ev[3]));
-    unsigned long long c[4];
+    unsigned long long c[8];
     CU(h, cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    out->traceback_rewalks = c[4];
     out->frames_ok = (uint32_t)c[0];
     out->frames_failed = (uint32_t)c[1];
     out->payload_bytes = c[2];

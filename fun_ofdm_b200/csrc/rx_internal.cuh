@@ -135,7 +135,7 @@ struct TracebackArgs {
     uint16_t *payload_len;
     uint8_t *rate_out;
     uint8_t *status_out;
-    unsigned long long *counters; // [0] frames ok, [1] frames failed, [2] payload bytes, [3] trellis steps
+    unsigned long long *counters; // [0] frames ok, [1] frames failed, [2] payload bytes, [3] trellis steps, [4] traceback re-walks
     uint8_t *dbg_decoded;
     uint32_t dbg_decoded_stride;
     uint32_t *dbg_field;

@@ -16,6 +16,7 @@ namespace {
 
 __constant__ uint32_t c_crc_tab[4][256]; // slice-by-4 tables of CRC-32/ISO-HDLC (reflected 0xEDB88320)
 __constant__ uint8_t c_scramble[127];    // descrambler bit per byte index mod 127 (ppdu.cpp:257-263)
+__constant__ uint32_t c_xpow[5][132];    // x^(8 * L * 2^lvl) mod P, reflected: CRC combine factors, L <= 129
 
 // ------------------------------------------------------------------------------------------------
 // Branch metrics from depunctured soft symbols (Viterbi-only entry point).
@@ -132,148 +133,245 @@ __global__ void __launch_bounds__(ACS2_WARPS * 32) viterbi_acs2_kernel(const Fra
 }
 
 // ------------------------------------------------------------------------------------------------
-// Traceback: one CTA per frame.  The chainback (viterbi.cpp:131-142) is a 12 000-step dependent
-// chain per frame; it is cut into tiles of TB_TILE decoded bits walked by different threads.
-// A tile starts TB_PRE steps later than it has to, from an arbitrary state (0), and relies on
-// survivor paths merging; this is then VERIFIED, not assumed: tile k is exact iff the state it had
-// at its upper boundary equals the state tile k+1 (already exact, by induction from the last tile,
-// which starts from the true end state 0) ended in.  Any tile failing the check is re-walked from
-// the right state, so the output always equals the sequential chainback bit for bit.
+// Traceback.  The chainback (viterbi.cpp:131-142) is a dependent chain of one step per decoded bit
+// (12 090 for a 1500-byte frame); it is cut into tiles of TB_TILE bits walked by different threads.
+// A tile starts TB_PRE steps later than it has to, from an arbitrary state (0), and relies on survivor
+// paths merging; this is then VERIFIED, not assumed: tile k is exact iff the state it had at its upper
+// boundary equals the state tile k+1 (already exact, by induction from the last tile, which starts from
+// the true end state 0) ended in.  A tile failing the check is re-walked from the right state, so the
+// output always equals the sequential chainback bit for bit (re-walks are counted: stats.traceback_rewalks).
+//
+// The walk runs in POSITION space: with q = rotr6^(tau % 6)(state at time tau) the survivor bit of the step
+// into tau sits at position q of row (tau-1)>>3, and going one step back only replaces bit
+// (6 - tau % 6) % 6 of q by that bit (the in-place butterfly of viterbi_acs2.cuh seen backwards).  Unrolled
+// over 24 steps every shift, row offset and byte store is a compile-time constant: ~12 instructions per step.
+// Survivor rows (64 B per 8 steps) are read straight from global memory: each thread uses its row for 8
+// consecutive steps (L1 hits) and prefetches the next one; the grid is persistent (TB_CTAS_PER_SM CTAs per
+// SM looping over frames) so that the rows in flight fit in L1.
 // ------------------------------------------------------------------------------------------------
 constexpr int TB_THREADS = 128;
-constexpr int TB_TILE = 96;  // decoded bits per tile (multiple of 8)
-constexpr int TB_PRE = 96;   // speculative pre-roll
-constexpr int TB_MAX_BYTES = 4224; // >= (8*(4095+6)+6+215)/8
+constexpr int TB_TILE = 96;         // decoded bits per tile (multiple of 24)
+constexpr int TB_PRE = 72;          // speculative pre-roll (multiple of 24)
+constexpr int TB_CTAS_PER_SM = 8;
+constexpr int TB_MAX_BYTES = 4224;  // >= (8*(4095+6)+6+215)/8
+constexpr int TB_MAX_TILES = (TB_MAX_BYTES * 8 + TB_TILE - 1) / TB_TILE; // 352
 
-__device__ __forceinline__ uint32_t walk_tile(const uint32_t *dec, uint32_t e, int n_from, int n_to, int out_below,
-                                              uint8_t *bytes, int entry_at, uint32_t *entry_state)
+__device__ __forceinline__ uint32_t tb_lookup(const uint32_t *row, uint32_t q, int t_and_7)
 {
-    // processes decoded-bit indices n = n_from-1 ... n_to (descending); survivor word of bit n is step n+6
-    for (int n = n_from - 1; n >= n_to; n--) {
-        if (n == entry_at) *entry_state = e >> 2;
-        const uint32_t k = acs2_decision_bit(dec, (uint32_t)n + 6u, e >> 2);
+    // word lane*2 + (reg>>1) = q >> 2; byte (reg&1)*2 + (1 - low) = (q ^ 1) & 3; bit 7 - (t & 7)
+    const uint32_t w = __ldg(row + (q >> 2));
+    return (w >> ((((q ^ 1u) & 3u) << 3) + (7u - (uint32_t)t_and_7))) & 1u;
+}
+
+// One backward step from time tau (dynamic phase).  dec: survivor words of the frame.
+__device__ __forceinline__ void tb_step_generic(const uint32_t *dec, int tau, uint32_t &q, uint32_t &e)
+{
+    const int t = tau - 1;
+    const uint32_t k = tb_lookup(dec + (size_t)(t >> 3) * ACS2_WORDS_PER_8, q, t & 7);
+    const int b = (6 - tau % 6) % 6;
+    q = (q & ~(1u << b)) | (k << b);
+    e = (e >> 1) | (k << 7);
+}
+
+// 24 backward steps for decoded bits n = 24m+23 ... 24m (times tau = 24m+30 ... 24m+7), all constants static.
+// `row0` = survivor row 3m (the row of step 24m).  Bytes 3m+2, 3m+1, 3m are complete at n = 24m+16, +8, +0.
+template <bool STORE>
+__device__ __forceinline__ void tb_block24(const uint32_t *row0, uint32_t &q, uint32_t &e, uint8_t *bytes3m)
+{
+#pragma unroll
+    for (int i = 23; i >= 0; i--) {
+        const int t = i + 6;                 // step index relative to 24m
+        const int tau = t + 1;
+        const uint32_t k = tb_lookup(row0 + (t >> 3) * ACS2_WORDS_PER_8, q, t & 7);
+        const int b = (6 - tau % 6) % 6;     // 24m is a multiple of 6
+        q = (q & ~(1u << b)) | (k << b);
         e = (e >> 1) | (k << 7);
-        if (n < out_below && (n & 7) == 0) bytes[n >> 3] = (uint8_t)e;
+        if (STORE && (i & 7) == 0) bytes3m[i >> 3] = (uint8_t)e;
     }
-    return e;
+}
+
+// Walks decoded bits n = n_from-1 ... n_to (n_to a multiple of 24) starting from state `state` at time
+// n_from + 6.  Bytes are stored for n < out_below.  Returns the state at time n_to + 6; *e_out gets the byte register.
+__device__ __forceinline__ uint32_t tb_walk(const uint32_t *dec, uint32_t state, int n_from, int n_to, int out_below,
+                                            uint8_t *bytes, int entry_at, uint32_t *entry_state)
+{
+    int tau = n_from + 6;
+    int r = tau % 6;
+    uint32_t q = ((state >> r) | (state << (6 - r))) & 63u;
+    uint32_t e = state << 2;
+    int n = n_from - 1;
+    // ragged top: single steps down to a multiple of 24
+    while ((n + 1) % 24 != 0 && n >= n_to) {
+        if (n == entry_at) { const int rr = (n + 7) % 6; *entry_state = ((q << rr) | (q >> (6 - rr))) & 63u; }
+        tb_step_generic(dec, n + 7, q, e);
+        if (n < out_below && (n & 7) == 0) bytes[n >> 3] = (uint8_t)e;
+        n--;
+    }
+    for (; n >= n_to; n -= 24) {
+        // n + 1 is a multiple of 24: block m = (n - 23) / 24
+        if (n == entry_at) { const int rr = (n + 7) % 6; *entry_state = ((q << rr) | (q >> (6 - rr))) & 63u; }
+        const int m3 = (n - 23) >> 3; // 3m
+        const uint32_t *row0 = dec + (size_t)m3 * ACS2_WORDS_PER_8;
+        if (m3 >= 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(row0 - 3 * ACS2_WORDS_PER_8)); // next block's top rows
+        if (n < out_below) tb_block24<true>(row0, q, e, bytes + m3);
+        else tb_block24<false>(row0, q, e, bytes + m3);
+    }
+    const int rr = (n_to + 6) % 6;
+    (void)e;
+    return ((q << rr) | (q >> (6 - rr))) & 63u;
+}
+
+// a(x) * b(x) mod P(x) in the reflected CRC-32 representation (bit 31 = x^0)
+__device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+#pragma unroll 4
+    for (int i = 31; i >= 0; i--) {
+        p ^= ((a >> i) & 1u) ? b : 0u;
+        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+    }
+    return p;
 }
 
 __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
 {
     __shared__ uint8_t s_bytes[TB_MAX_BYTES];
-    __shared__ uint8_t s_entry[512], s_exit[512];
+    __shared__ uint8_t s_entry[TB_MAX_TILES + 1], s_exit[TB_MAX_TILES + 1];
     __shared__ uint32_t s_crc[4][256];
-    __shared__ int s_status;
+    __shared__ uint32_t s_flag;
 
-    const uint32_t frame = blockIdx.x;
     const int tid = threadIdx.x;
-    FrameDesc d = a.desc[frame];
-    const int nbits = (int)d.data_bits;
-
-    if (d.status != B200RX_ST_OK || nbits <= 0) {
-        if (tid == 0) {
-            if (a.status_out) a.status_out[frame] = d.status;
-            if (a.payload_len) a.payload_len[frame] = (d.status == B200RX_ST_TRUNCATED || d.status == B200RX_ST_TOO_LONG) ? d.length : 0;
-            if (a.rate_out) a.rate_out[frame] = d.rate;
-            if (a.dbg_field) a.dbg_field[frame] = d.field;
-            if (a.counters) atomicAdd(&a.counters[1], 1ull);
-        }
-        return;
-    }
-
     if (!a.raw_mode)
         for (int i = tid; i < 1024; i += TB_THREADS) (&s_crc[0][0])[i] = (&c_crc_tab[0][0])[i];
 
-    const uint32_t *dec = a.dec + (size_t)frame * a.dec_stride;
-    const int nbytes = (nbits + 7) >> 3;
-    const int ntiles = (nbits + TB_TILE - 1) / TB_TILE;
+    for (uint32_t frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
+        __syncthreads(); // shared buffers of the previous frame are free
+        const FrameDesc d = a.desc[frame];
+        const int nbits = (int)d.data_bits;
 
-    for (int k = tid; k < ntiles; k += TB_THREADS) {
-        const int lo = k * TB_TILE;
-        const int hi = min(lo + TB_TILE, nbits);
-        const int from = min(hi + TB_PRE, nbits);
-        uint32_t entry = 0; // state at the tile's upper boundary (true value 0 when hi == nbits)
-        const uint32_t e = walk_tile(dec, 0u, from, lo, hi, s_bytes, hi - 1, &entry);
-        s_entry[k] = (uint8_t)entry;
-        s_exit[k] = (uint8_t)(e >> 2);
-    }
-    __syncthreads();
+        if (d.status != B200RX_ST_OK || nbits <= 0) {
+            if (tid == 0) {
+                if (a.status_out) a.status_out[frame] = d.status;
+                if (a.payload_len) a.payload_len[frame] = (d.status == B200RX_ST_TRUNCATED || d.status == B200RX_ST_TOO_LONG) ? d.length : 0;
+                if (a.rate_out) a.rate_out[frame] = d.rate;
+                if (a.dbg_field) a.dbg_field[frame] = d.field;
+                if (a.counters) atomicAdd(&a.counters[1], 1ull);
+            }
+            continue;
+        }
 
-    if (tid == 0) {
-        for (int k = ntiles - 2; k >= 0; k--) {
-            if (s_entry[k] != s_exit[k + 1]) { // paths had not merged: redo from the verified state
-                const int lo = k * TB_TILE, hi = lo + TB_TILE;
-                uint32_t dummy;
-                const uint32_t e = walk_tile(dec, (uint32_t)s_exit[k + 1] << 2, hi, lo, hi, s_bytes, -1, &dummy);
-                s_exit[k] = (uint8_t)(e >> 2);
+        const uint32_t *dec = a.dec + (size_t)frame * a.dec_stride;
+        const int nbytes = (nbits + 7) >> 3;
+        const int ntiles = (nbits + TB_TILE - 1) / TB_TILE;
+
+        for (int k = tid; k < ntiles; k += TB_THREADS) {
+            const int lo = k * TB_TILE;
+            const int hi = min(lo + TB_TILE, nbits);
+            const int from = min(hi + TB_PRE, nbits);
+            uint32_t entry = 0; // state at the tile's upper boundary (true value 0 when hi == nbits)
+            const uint32_t ex = tb_walk(dec, 0u, from, lo, hi, s_bytes, hi - 1, &entry);
+            s_entry[k] = (uint8_t)entry;
+            s_exit[k] = (uint8_t)ex;
+        }
+        __syncthreads();
+
+        // verify the chain in parallel; only if some tile had not merged, repair serially from the top
+        int bad = 0;
+        for (int k = tid; k < ntiles - 1; k += TB_THREADS) bad |= (s_entry[k] != s_exit[k + 1]);
+        if (__syncthreads_or(bad)) {
+            if (tid == 0) {
+                unsigned rewalks = 0;
+                for (int k = ntiles - 2; k >= 0; k--) {
+                    if (s_entry[k] != s_exit[k + 1]) {
+                        const int lo = k * TB_TILE, hi = lo + TB_TILE;
+                        uint32_t dummy;
+                        s_exit[k] = (uint8_t)tb_walk(dec, (uint32_t)s_exit[k + 1], hi, lo, hi, s_bytes, -1, &dummy);
+                        s_entry[k] = s_exit[k + 1];
+                        rewalks++;
+                    }
+                }
+                if (a.counters) atomicAdd(&a.counters[4], (unsigned long long)rewalks);
+            }
+            __syncthreads();
+        }
+
+        if (a.dbg_decoded)
+            for (int i = tid; i < nbytes && i < (int)a.dbg_decoded_stride; i += TB_THREADS)
+                a.dbg_decoded[(size_t)frame * a.dbg_decoded_stride + i] = s_bytes[i];
+
+        if (a.raw_mode) {
+            for (int i = tid; i < nbytes && i < (int)a.payload_stride; i += TB_THREADS)
+                a.payload[(size_t)frame * a.payload_stride + i] = s_bytes[i];
+            if (tid == 0) {
+                if (a.status_out) a.status_out[frame] = B200RX_ST_OK;
+                if (a.counters) { atomicAdd(&a.counters[0], 1ull); atomicAdd(&a.counters[3], (unsigned long long)d.n_steps); }
+            }
+            continue;
+        }
+
+        // ppdu.cpp:255-264: num_data_bytes = (nsym*dbps)/8 bytes descrambled; bit 0 of byte x flipped by
+        // the LFSR output of step x (state 93, one step per byte, period 127)
+        const int num_data_bytes = (int)(d.n_steps >> 3);
+        for (int i = tid; i < num_data_bytes && i < nbytes; i += TB_THREADS) s_bytes[i] ^= c_scramble[i % 127];
+        __syncthreads();
+
+        // ppdu.cpp:267-279: CRC-32 over service(2) + payload, against the little-endian word behind it.
+        // Warp-parallel: 32 right-aligned segments of L bytes (the first may be shorter or empty), each lane
+        // takes the standard CRC of its segment, then a 5-level tree of crc(A||B) = crc(A)*x^(8|B|) ^ crc(B).
+        const int len = d.length;
+        const int n = 2 + len;
+        if (tid < 32) {
+            const int L = (n + 31) >> 5;
+            const int beg = max(0, n - (32 - tid) * L), end = max(0, n - (31 - tid) * L);
+            uint32_t r = 0xFFFFFFFFu;
+            int i = beg;
+            for (; i + 4 <= end; i += 4) {
+                r ^= (uint32_t)s_bytes[i] | ((uint32_t)s_bytes[i + 1] << 8) | ((uint32_t)s_bytes[i + 2] << 16) |
+                     ((uint32_t)s_bytes[i + 3] << 24);
+                r = s_crc[3][r & 0xFF] ^ s_crc[2][(r >> 8) & 0xFF] ^ s_crc[1][(r >> 16) & 0xFF] ^ s_crc[0][r >> 24];
+            }
+            for (; i < end; i++) r = s_crc[0][(r ^ s_bytes[i]) & 0xFF] ^ (r >> 8);
+            uint32_t crc = (end > beg) ? (r ^ 0xFFFFFFFFu) : 0u; // CRC of the empty string is 0
+#pragma unroll
+            for (int lvl = 0; lvl < 5; lvl++) {
+                const uint32_t right = __shfl_down_sync(0xFFFFFFFFu, crc, 1 << lvl);
+                if ((tid & ((2 << lvl) - 1)) == 0) crc = crc_multmodp(c_xpow[lvl][L], crc) ^ right;
+            }
+            if (tid == 0) {
+                const uint32_t given = (uint32_t)s_bytes[n] | ((uint32_t)s_bytes[n + 1] << 8) |
+                                       ((uint32_t)s_bytes[n + 2] << 16) | ((uint32_t)s_bytes[n + 3] << 24);
+                s_flag = (crc == given) ? B200RX_ST_OK : B200RX_ST_CRC_FAIL;
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
+        const int status = (int)s_flag;
 
-    if (a.dbg_decoded)
-        for (int i = tid; i < nbytes && i < (int)a.dbg_decoded_stride; i += TB_THREADS)
-            a.dbg_decoded[(size_t)frame * a.dbg_decoded_stride + i] = s_bytes[i];
-
-    if (a.raw_mode) {
-        for (int i = tid; i < nbytes && i < (int)a.payload_stride; i += TB_THREADS)
-            a.payload[(size_t)frame * a.payload_stride + i] = s_bytes[i];
+        // payload = descrambled[2 .. 2+len) (ppdu.cpp:284-285); written for CRC failures too (status says so)
+        if (a.payload)
+            for (int i = tid; i < len && i < (int)a.payload_stride; i += TB_THREADS)
+                a.payload[(size_t)frame * a.payload_stride + i] = s_bytes[2 + i];
         if (tid == 0) {
-            if (a.status_out) a.status_out[frame] = B200RX_ST_OK;
-            if (a.counters) { atomicAdd(&a.counters[0], 1ull); atomicAdd(&a.counters[3], (unsigned long long)d.n_steps); }
-        }
-        return;
-    }
-
-    // ppdu.cpp:255-264: num_data_bytes = (nsym*dbps)/8 bytes descrambled; bit 0 of byte x flipped by
-    // the LFSR output of step x (state 93, one step per byte, period 127)
-    const int num_data_bytes = (int)(d.n_steps >> 3);
-    for (int i = tid; i < num_data_bytes && i < nbytes; i += TB_THREADS) s_bytes[i] ^= c_scramble[i % 127];
-    __syncthreads();
-
-    // ppdu.cpp:267-279: CRC-32 over service(2) + payload, against the little-endian word behind it
-    const int len = d.length;
-    if (tid == 0) {
-        uint32_t r = 0xFFFFFFFFu;
-        const int n = 2 + len;
-        int i = 0;
-        for (; i + 4 <= n; i += 4) {
-            r ^= (uint32_t)s_bytes[i] | ((uint32_t)s_bytes[i + 1] << 8) | ((uint32_t)s_bytes[i + 2] << 16) |
-                 ((uint32_t)s_bytes[i + 3] << 24);
-            r = s_crc[3][r & 0xFF] ^ s_crc[2][(r >> 8) & 0xFF] ^ s_crc[1][(r >> 16) & 0xFF] ^ s_crc[0][r >> 24];
-        }
-        for (; i < n; i++) r = s_crc[0][(r ^ s_bytes[i]) & 0xFF] ^ (r >> 8);
-        r ^= 0xFFFFFFFFu;
-        const uint32_t given = (uint32_t)s_bytes[n] | ((uint32_t)s_bytes[n + 1] << 8) |
-                               ((uint32_t)s_bytes[n + 2] << 16) | ((uint32_t)s_bytes[n + 3] << 24);
-        s_status = (r == given) ? B200RX_ST_OK : B200RX_ST_CRC_FAIL;
-    }
-    __syncthreads();
-    const int status = s_status;
-
-    // payload = descrambled[2 .. 2+len) (ppdu.cpp:284-285); written for CRC failures too (status says so)
-    if (a.payload)
-        for (int i = tid; i < len && i < (int)a.payload_stride; i += TB_THREADS)
-            a.payload[(size_t)frame * a.payload_stride + i] = s_bytes[2 + i];
-    if (tid == 0) {
-        if (a.status_out) a.status_out[frame] = (uint8_t)status;
-        if (a.payload_len) a.payload_len[frame] = (uint16_t)len;
-        if (a.rate_out) a.rate_out[frame] = d.rate;
-        if (a.dbg_field) a.dbg_field[frame] = d.field;
-        a.desc[frame].status = (uint8_t)status;
-        if (a.counters) {
-            atomicAdd(&a.counters[status == B200RX_ST_OK ? 0 : 1], 1ull);
-            if (status == B200RX_ST_OK) atomicAdd(&a.counters[2], (unsigned long long)len);
-            atomicAdd(&a.counters[3], (unsigned long long)d.n_steps);
+            if (a.status_out) a.status_out[frame] = (uint8_t)status;
+            if (a.payload_len) a.payload_len[frame] = (uint16_t)len;
+            if (a.rate_out) a.rate_out[frame] = d.rate;
+            if (a.dbg_field) a.dbg_field[frame] = d.field;
+            a.desc[frame].status = (uint8_t)status;
+            if (a.counters) {
+                atomicAdd(&a.counters[status == B200RX_ST_OK ? 0 : 1], 1ull);
+                if (status == B200RX_ST_OK) atomicAdd(&a.counters[2], (unsigned long long)len);
+                atomicAdd(&a.counters[3], (unsigned long long)d.n_steps);
+            }
         }
     }
 }
 
 } // namespace
 
-cudaError_t upload_viterbi_tables(const uint32_t *crc, const uint8_t *scr)
+cudaError_t upload_viterbi_tables(const uint32_t *crc, const uint8_t *scr, const uint32_t *xpow)
 {
     cudaError_t e = cudaMemcpyToSymbol(c_crc_tab, crc, sizeof(uint32_t) * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_xpow, xpow, sizeof(uint32_t) * 5 * 132);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_scramble, scr, 127);
 }
@@ -323,7 +421,15 @@ cudaError_t launch_export_headers(const FrameDesc *desc, uint32_t n, uint16_t *l
 cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s)
 {
     if (a.n_frames == 0) return cudaSuccess;
-    traceback_kernel<<<a.n_frames, TB_THREADS, 0, s>>>(a);
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const uint32_t grid = min((uint32_t)(n_sm * TB_CTAS_PER_SM), a.n_frames);
+    traceback_kernel<<<grid, TB_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -44,7 +44,8 @@ class Debug(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("frontend_ms", C.c_float), ("viterbi_ms", C.c_float), ("traceback_ms", C.c_float),
                 ("total_ms", C.c_float), ("trellis_steps", C.c_uint64), ("frames_ok", C.c_uint32),
-                ("frames_failed", C.c_uint32), ("payload_bytes", C.c_uint64)]
+                ("frames_failed", C.c_uint32), ("payload_bytes", C.c_uint64),
+                ("traceback_rewalks", C.c_uint64)]
 
 
 def lib_path():

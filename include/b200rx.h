@@ -91,6 +91,7 @@ typedef struct {
     uint32_t frames_ok;
     uint32_t frames_failed;
     uint64_t payload_bytes; /* of CRC-OK frames */
+    uint64_t traceback_rewalks; /* traceback tiles whose speculative pre-roll had not merged and were redone */
 } b200rx_stats;
 
 /* Lifetime.  One handle per GPU per host thread; a handle is not re-entrant. */
