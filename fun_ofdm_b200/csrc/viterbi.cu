@@ -145,44 +145,52 @@ __global__ void __launch_bounds__(ACS2_WARPS * 32) viterbi_acs2_kernel(const Fra
 // into tau sits at position q of row (tau-1)>>3, and going one step back only replaces bit
 // (6 - tau % 6) % 6 of q by that bit (the in-place butterfly of viterbi_acs2.cuh seen backwards).  Unrolled
 // over 24 steps every shift, row offset and byte store is a compile-time constant: ~12 instructions per step.
-// Survivor rows (64 B per 8 steps) are read straight from global memory: each thread uses its row for 8
-// consecutive steps (L1 hits) and prefetches the next one; the grid is persistent (TB_CTAS_PER_SM CTAs per
-// SM looping over frames) so that the rows in flight fit in L1.
+//
+// Memory: 32 tiles of a warp sit 768 B apart, so reading survivor words straight from global memory costs
+// 32 L1 wavefronts per warp load and the kernel is L1-pipeline bound (ncu r01: issue 16 %, long_scoreboard
+// 30).  Instead the CTA works in rounds of 24 steps: the four 64-byte survivor rows every tile needs for its
+// next 24 steps are copied to shared memory with coalesced 16-byte cp.async (256 B contiguous per tile),
+// then each thread walks its 24 steps out of shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int TB_THREADS = 128;
 constexpr int TB_TILE = 96;         // decoded bits per tile (multiple of 24)
 constexpr int TB_PRE = 72;          // speculative pre-roll (multiple of 24)
-constexpr int TB_CTAS_PER_SM = 8;
+constexpr int TB_ROUNDS = (TB_TILE + TB_PRE) / 24;
+constexpr int TB_CTAS_PER_SM = 5;
+constexpr int TB_ROW_W = 20;        // words per staged row (16 used; 80 B keeps cp.async 16-byte aligned)
+constexpr int TB_TILE_W = 4 * TB_ROW_W + 4; // words per tile slot; 84 spreads the 32 lanes of a warp over the banks
 constexpr int TB_MAX_BYTES = 4224;  // >= (8*(4095+6)+6+215)/8
 constexpr int TB_MAX_TILES = (TB_MAX_BYTES * 8 + TB_TILE - 1) / TB_TILE; // 352
 
+template <bool GLOBAL>
 __device__ __forceinline__ uint32_t tb_lookup(const uint32_t *row, uint32_t q, int t_and_7)
 {
     // word lane*2 + (reg>>1) = q >> 2; byte (reg&1)*2 + (1 - low) = (q ^ 1) & 3; bit 7 - (t & 7)
-    const uint32_t w = __ldg(row + (q >> 2));
+    const uint32_t w = GLOBAL ? __ldg(row + (q >> 2)) : row[q >> 2];
     return (w >> ((((q ^ 1u) & 3u) << 3) + (7u - (uint32_t)t_and_7))) & 1u;
 }
 
-// One backward step from time tau (dynamic phase).  dec: survivor words of the frame.
+// One backward step from time tau (dynamic phase), survivor words read from global memory.
 __device__ __forceinline__ void tb_step_generic(const uint32_t *dec, int tau, uint32_t &q, uint32_t &e)
 {
     const int t = tau - 1;
-    const uint32_t k = tb_lookup(dec + (size_t)(t >> 3) * ACS2_WORDS_PER_8, q, t & 7);
+    const uint32_t k = tb_lookup<true>(dec + (size_t)(t >> 3) * ACS2_WORDS_PER_8, q, t & 7);
     const int b = (6 - tau % 6) % 6;
     q = (q & ~(1u << b)) | (k << b);
     e = (e >> 1) | (k << 7);
 }
 
 // 24 backward steps for decoded bits n = 24m+23 ... 24m (times tau = 24m+30 ... 24m+7), all constants static.
-// `row0` = survivor row 3m (the row of step 24m).  Bytes 3m+2, 3m+1, 3m are complete at n = 24m+16, +8, +0.
-template <bool STORE>
+// `row0` = survivor row 3m (the row of step 24m), rows ROW_W words apart.  Bytes 3m+2, 3m+1, 3m are complete at
+// n = 24m+16, +8, +0.
+template <bool GLOBAL, int ROW_W, bool STORE>
 __device__ __forceinline__ void tb_block24(const uint32_t *row0, uint32_t &q, uint32_t &e, uint8_t *bytes3m)
 {
 #pragma unroll
     for (int i = 23; i >= 0; i--) {
         const int t = i + 6;                 // step index relative to 24m
         const int tau = t + 1;
-        const uint32_t k = tb_lookup(row0 + (t >> 3) * ACS2_WORDS_PER_8, q, t & 7);
+        const uint32_t k = tb_lookup<GLOBAL>(row0 + (t >> 3) * ROW_W, q, t & 7);
         const int b = (6 - tau % 6) % 6;     // 24m is a multiple of 6
         q = (q & ~(1u << b)) | (k << b);
         e = (e >> 1) | (k << 7);
@@ -190,35 +198,38 @@ __device__ __forceinline__ void tb_block24(const uint32_t *row0, uint32_t &q, ui
     }
 }
 
-// Walks decoded bits n = n_from-1 ... n_to (n_to a multiple of 24) starting from state `state` at time
-// n_from + 6.  Bytes are stored for n < out_below.  Returns the state at time n_to + 6; *e_out gets the byte register.
-__device__ __forceinline__ uint32_t tb_walk(const uint32_t *dec, uint32_t state, int n_from, int n_to, int out_below,
-                                            uint8_t *bytes, int entry_at, uint32_t *entry_state)
+__device__ __forceinline__ uint32_t tb_state_to_pos(uint32_t state, int tau)
 {
-    int tau = n_from + 6;
-    int r = tau % 6;
-    uint32_t q = ((state >> r) | (state << (6 - r))) & 63u;
-    uint32_t e = state << 2;
+    const int r = tau % 6;
+    return ((state >> r) | (state << (6 - r))) & 63u;
+}
+__device__ __forceinline__ uint32_t tb_pos_to_state(uint32_t q, int tau)
+{
+    const int r = tau % 6;
+    return ((q << r) | (q >> (6 - r))) & 63u;
+}
+
+// Serial repair walk (rare): decoded bits n = n_from-1 ... n_to from a known state, straight from global memory.
+__device__ __forceinline__ uint32_t tb_walk_global(const uint32_t *dec, uint32_t state, int n_from, int n_to,
+                                                   uint8_t *bytes)
+{
+    uint32_t q = tb_state_to_pos(state, n_from + 6), e = state << 2;
     int n = n_from - 1;
-    // ragged top: single steps down to a multiple of 24
-    while ((n + 1) % 24 != 0 && n >= n_to) {
-        if (n == entry_at) { const int rr = (n + 7) % 6; *entry_state = ((q << rr) | (q >> (6 - rr))) & 63u; }
+    for (; (n + 1) % 24 != 0 && n >= n_to; n--) {
         tb_step_generic(dec, n + 7, q, e);
-        if (n < out_below && (n & 7) == 0) bytes[n >> 3] = (uint8_t)e;
-        n--;
+        if ((n & 7) == 0) bytes[n >> 3] = (uint8_t)e;
     }
     for (; n >= n_to; n -= 24) {
-        // n + 1 is a multiple of 24: block m = (n - 23) / 24
-        if (n == entry_at) { const int rr = (n + 7) % 6; *entry_state = ((q << rr) | (q >> (6 - rr))) & 63u; }
-        const int m3 = (n - 23) >> 3; // 3m
-        const uint32_t *row0 = dec + (size_t)m3 * ACS2_WORDS_PER_8;
-        if (m3 >= 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(row0 - 3 * ACS2_WORDS_PER_8)); // next block's top rows
-        if (n < out_below) tb_block24<true>(row0, q, e, bytes + m3);
-        else tb_block24<false>(row0, q, e, bytes + m3);
+        const int m3 = (n - 23) >> 3;
+        tb_block24<true, ACS2_WORDS_PER_8, true>(dec + (size_t)m3 * ACS2_WORDS_PER_8, q, e, bytes + m3);
     }
-    const int rr = (n_to + 6) % 6;
-    (void)e;
-    return ((q << rr) | (q >> (6 - rr))) & 63u;
+    return tb_pos_to_state(q, n_to + 6);
+}
+
+__device__ __forceinline__ void tb_cp_async16(uint32_t *smem_dst, const uint32_t *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
 }
 
 // a(x) * b(x) mod P(x) in the reflected CRC-32 representation (bit 31 = x^0)
@@ -235,6 +246,7 @@ __device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
 
 __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
 {
+    extern __shared__ __align__(16) uint32_t s_rows[]; // TB_THREADS * TB_TILE_W words (dynamic: > 48 KB with the rest)
     __shared__ uint8_t s_bytes[TB_MAX_BYTES];
     __shared__ uint8_t s_entry[TB_MAX_TILES + 1], s_exit[TB_MAX_TILES + 1];
     __shared__ uint32_t s_crc[4][256];
@@ -264,14 +276,51 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
         const int nbytes = (nbits + 7) >> 3;
         const int ntiles = (nbits + TB_TILE - 1) / TB_TILE;
 
-        for (int k = tid; k < ntiles; k += TB_THREADS) {
+        for (int g = 0; g * TB_THREADS < ntiles; g++) {
+            const int k = g * TB_THREADS + tid;
+            const bool active = k < ntiles;
             const int lo = k * TB_TILE;
             const int hi = min(lo + TB_TILE, nbits);
             const int from = min(hi + TB_PRE, nbits);
-            uint32_t entry = 0; // state at the tile's upper boundary (true value 0 when hi == nbits)
-            const uint32_t ex = tb_walk(dec, 0u, from, lo, hi, s_bytes, hi - 1, &entry);
-            s_entry[k] = (uint8_t)entry;
-            s_exit[k] = (uint8_t)ex;
+            uint32_t q = 0, e = 0, entry = 0; // start state 0 (true when from == nbits, a guess otherwise)
+            int n = from - 1;
+            if (active) {
+                q = tb_state_to_pos(0u, from + 6);
+                // ragged top (only tiles within TB_PRE of the end of the frame): single steps from global memory
+                for (; (n + 1) % 24 != 0 && n >= lo; n--) {
+                    if (n == hi - 1) entry = tb_pos_to_state(q, n + 7);
+                    tb_step_generic(dec, n + 7, q, e);
+                    if (n < hi && (n & 7) == 0) s_bytes[n >> 3] = (uint8_t)e;
+                }
+            }
+            for (int round = 0; round < TB_ROUNDS; round++) {
+                __syncthreads(); // everybody is done with the rows of the previous round
+                // stage rows 3m .. 3m+3 of every tile's next block m: 16 pieces of 16 B per tile
+                for (int i = tid; i < TB_THREADS * 16; i += TB_THREADS) {
+                    const int tile = i >> 4, part = i & 15;
+                    const int tk = g * TB_THREADS + tile;
+                    const int tlo = tk * TB_TILE;
+                    const int tfrom = min(min(tlo + TB_TILE, nbits) + TB_PRE, nbits);
+                    const int tm = tfrom / 24 - 1 - round; // block index this tile walks in this round
+                    if (tk < ntiles && tm * 24 >= tlo)
+                        tb_cp_async16(s_rows + tile * TB_TILE_W + (part >> 2) * TB_ROW_W + (part & 3) * 4,
+                                      dec + (size_t)(3 * tm) * ACS2_WORDS_PER_8 + part * 4);
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();
+                if (active && n >= lo) {
+                    if (n == hi - 1) entry = tb_pos_to_state(q, n + 7);
+                    const int m3 = (n - 23) >> 3;
+                    const uint32_t *row0 = s_rows + tid * TB_TILE_W;
+                    if (n < hi) tb_block24<false, TB_ROW_W, true>(row0, q, e, s_bytes + m3);
+                    else tb_block24<false, TB_ROW_W, false>(row0, q, e, s_bytes + m3);
+                    n -= 24;
+                }
+            }
+            if (active) {
+                s_entry[k] = (uint8_t)entry;
+                s_exit[k] = (uint8_t)tb_pos_to_state(q, lo + 6);
+            }
         }
         __syncthreads();
 
@@ -284,8 +333,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
                 for (int k = ntiles - 2; k >= 0; k--) {
                     if (s_entry[k] != s_exit[k + 1]) {
                         const int lo = k * TB_TILE, hi = lo + TB_TILE;
-                        uint32_t dummy;
-                        s_exit[k] = (uint8_t)tb_walk(dec, (uint32_t)s_exit[k + 1], hi, lo, hi, s_bytes, -1, &dummy);
+                        s_exit[k] = (uint8_t)tb_walk_global(dec, (uint32_t)s_exit[k + 1], hi, lo, s_bytes);
                         s_entry[k] = s_exit[k + 1];
                         rewalks++;
                     }
@@ -428,8 +476,15 @@ cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s)
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm <= 0) n_sm = 148;
     }
+    constexpr size_t dyn = sizeof(uint32_t) * TB_THREADS * TB_TILE_W;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     const uint32_t grid = min((uint32_t)(n_sm * TB_CTAS_PER_SM), a.n_frames);
-    traceback_kernel<<<grid, TB_THREADS, 0, s>>>(a);
+    traceback_kernel<<<grid, TB_THREADS, dyn, s>>>(a);
     return cudaGetLastError();
 }
 
