@@ -43,6 +43,10 @@ struct b200rx_handle {
     uint8_t *d_rate = nullptr;
     uint8_t *d_status = nullptr;
 
+    // host-buffer pipeline: H2D of chunk i+1 overlaps the kernels of chunk i
+    cudaStream_t copy_stream = nullptr, aux_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> pipe_ev; // 2 per chunk: samples landed, results ready
+
     uint64_t launches = 0;
     std::string error;
 };
@@ -191,6 +195,9 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
     A((void **)&h->desc, nf * sizeof(FrameDesc));
     A((void **)&h->bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
@@ -222,6 +229,10 @@ int b200rx_destroy(b200rx_handle *h)
     cudaFree(h->d_len); cudaFree(h->d_rate); cudaFree(h->d_status);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->pipe_ev) if (e) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return B200RX_OK;
@@ -266,6 +277,64 @@ int b200rx_device_counters(b200rx_handle *h, void **dev_ptr)
 uint64_t b200rx_launch_count(const b200rx_handle *h) { return h ? h->launches : 0; }
 uint32_t b200rx_max_steps(const b200rx_handle *h) { return h ? h->max_steps : 0; }
 
+namespace {
+
+struct OutPtrs { uint8_t *payload; uint32_t stride; uint16_t *len; uint8_t *rate; uint8_t *status; };
+
+// K1 -> K2 -> K3 for frames [off, off + n) of the batch on stream s; ev (4 events) optional.
+int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, const double *iq_dev, uint64_t iq_samples,
+                 const uint64_t *lts1_dev, const uint32_t *avail_dev, const OutPtrs &o, const b200rx_debug *dbg,
+                 cudaEvent_t *ev)
+{
+    const size_t S = h->max_steps;
+    FrontendArgs fa{};
+    fa.iq = reinterpret_cast<const double2 *>(iq_dev);
+    fa.iq_samples = iq_samples;
+    fa.lts1 = lts1_dev + off;
+    fa.avail = avail_dev + off;
+    fa.n_frames = n;
+    fa.desc = h->desc + off;
+    fa.bm = h->bm + (size_t)off * S;
+    fa.bm_stride = h->max_steps;
+    fa.max_steps = h->max_steps;
+    fa.max_len = h->limits.max_payload_bytes;
+    if (dbg) {
+        fa.dbg_eq = dbg->equalized ? reinterpret_cast<double2 *>(dbg->equalized) + (size_t)off * dbg->eq_vectors * 48 : nullptr;
+        fa.dbg_eq_vectors = dbg->eq_vectors;
+        fa.dbg_depunct = dbg->depunct ? dbg->depunct + (size_t)off * dbg->depunct_stride : nullptr;
+        fa.dbg_depunct_stride = dbg->depunct_stride;
+    }
+    if (ev) CU(h, cudaEventRecord(ev[0], s));
+    CU(h, launch_frontend(fa, s));
+    if (ev) CU(h, cudaEventRecord(ev[1], s));
+    CU(h, launch_viterbi_acs(h->desc + off, h->bm + (size_t)off * S, h->max_steps, h->dec + (size_t)off * 2 * S,
+                             2 * h->max_steps, n, s));
+    if (ev) CU(h, cudaEventRecord(ev[2], s));
+    TracebackArgs ta{};
+    ta.desc = h->desc + off;
+    ta.dec = h->dec + (size_t)off * 2 * S;
+    ta.dec_stride = 2 * h->max_steps;
+    ta.n_frames = n;
+    ta.raw_mode = 0;
+    ta.payload = o.payload ? o.payload + (size_t)off * o.stride : nullptr;
+    ta.payload_stride = o.stride;
+    ta.payload_len = o.len ? o.len + off : nullptr;
+    ta.rate_out = o.rate ? o.rate + off : nullptr;
+    ta.status_out = o.status + off;
+    ta.counters = h->counters;
+    if (dbg) {
+        ta.dbg_decoded = dbg->decoded ? dbg->decoded + (size_t)off * dbg->decoded_stride : nullptr;
+        ta.dbg_decoded_stride = dbg->decoded_stride;
+        ta.dbg_field = dbg->header_field ? dbg->header_field + off : nullptr;
+    }
+    CU(h, launch_traceback(ta, s));
+    if (ev) CU(h, cudaEventRecord(ev[3], s));
+    h->launches += 3;
+    return B200RX_OK;
+}
+
+} // namespace
+
 int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_samples,
                             const uint64_t *lts1_index_dev, const uint32_t *avail_dev, uint32_t n_frames,
                             uint8_t *payload_out_dev, uint32_t payload_stride,
@@ -282,51 +351,10 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
 
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     cudaEvent_t *ev = call_events(h);
-    CU(h, cudaEventRecord(ev[0], s));
-
-    FrontendArgs fa{};
-    fa.iq = reinterpret_cast<const double2 *>(iq_dev);
-    fa.iq_samples = iq_samples;
-    fa.lts1 = lts1_index_dev;
-    fa.avail = avail_dev;
-    fa.n_frames = n_frames;
-    fa.desc = h->desc;
-    fa.bm = h->bm;
-    fa.bm_stride = h->max_steps;
-    fa.max_steps = h->max_steps;
-    fa.max_len = h->limits.max_payload_bytes;
-    if (dbg) {
-        fa.dbg_eq = reinterpret_cast<double2 *>(dbg->equalized);
-        fa.dbg_eq_vectors = dbg->eq_vectors;
-        fa.dbg_depunct = dbg->depunct;
-        fa.dbg_depunct_stride = dbg->depunct_stride;
-    }
-    CU(h, launch_frontend(fa, s));
-    CU(h, cudaEventRecord(ev[1], s));
-    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, 2 * h->max_steps, n_frames, s));
-    CU(h, cudaEventRecord(ev[2], s));
-
-    TracebackArgs ta{};
-    ta.desc = h->desc;
-    ta.dec = h->dec;
-    ta.dec_stride = 2 * h->max_steps;
-    ta.n_frames = n_frames;
-    ta.raw_mode = 0;
-    ta.payload = payload_out_dev;
-    ta.payload_stride = payload_stride;
-    ta.payload_len = payload_len_dev;
-    ta.rate_out = rate_out_dev;
-    ta.status_out = status_dev;
-    ta.counters = h->counters;
-    if (dbg) {
-        ta.dbg_decoded = dbg->decoded;
-        ta.dbg_decoded_stride = dbg->decoded_stride;
-        ta.dbg_field = dbg->header_field;
-    }
-    CU(h, launch_traceback(ta, s));
-    CU(h, cudaEventRecord(ev[3], s));
+    const OutPtrs o{payload_out_dev, payload_stride, payload_len_dev, rate_out_dev, status_dev};
+    int rc = launch_range(h, s, 0, n_frames, iq_dev, iq_samples, lts1_index_dev, avail_dev, o, dbg, ev);
+    if (rc != B200RX_OK) return rc;
     if (ev == h->ev) h->ev_valid = true;
-    h->launches += 3;
     return B200RX_OK;
 }
 
@@ -356,17 +384,72 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
         if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_decode_batch: payload staging", e);
         h->d_payload_cap = pl_bytes;
     }
-    CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
     CU(h, cudaMemcpyAsync(h->d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CU(h, cudaMemcpyAsync(h->d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    int rc = b200rx_decode_batch_dev(h, h->d_iq, iq_samples, h->d_lts1, h->d_avail, n_frames,
-                                     payload_out ? h->d_payload : nullptr, payload_stride, h->d_len, h->d_rate,
-                                     h->d_status, nullptr);
-    if (rc != B200RX_OK) return rc;
-    if (payload_out) CU(h, cudaMemcpyAsync(payload_out, h->d_payload, pl_bytes, cudaMemcpyDeviceToHost, s));
-    if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
-    if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, n_frames, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(status, h->d_status, n_frames, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
+    const OutPtrs o{payload_out ? h->d_payload : nullptr, payload_stride, h->d_len, h->d_rate, h->d_status};
+
+    // Chunked pipeline: the samples of chunk i+1 cross PCIe while chunk i is decoded (kernels of consecutive
+    // chunks alternate between two streams so that their Viterbi kernels overlap) and chunk i-1's results go
+    // back.  Needs the frames in stream order (lts1_index non-decreasing); otherwise one copy, one batch.
+    const uint32_t CH = 512;
+    bool ordered = n_frames > CH;
+    for (uint32_t f = 1; ordered && f < n_frames; f++) ordered = lts1_index[f] >= lts1_index[f - 1];
+    if (!ordered) {
+        CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+        int rc = launch_range(h, s, 0, n_frames, h->d_iq, iq_samples, h->d_lts1, h->d_avail, o, nullptr, nullptr);
+        if (rc != B200RX_OK) return rc;
+        if (payload_out) CU(h, cudaMemcpyAsync(payload_out, h->d_payload, pl_bytes, cudaMemcpyDeviceToHost, s));
+        if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+        if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, n_frames, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(status, h->d_status, n_frames, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        return B200RX_OK;
+    }
+    const uint32_t n_chunks = (n_frames + CH - 1) / CH;
+    while (h->pipe_ev.size() < 2 * (size_t)n_chunks + 1) {
+        cudaEvent_t e;
+        CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pipe_ev.push_back(e);
+    }
+    cudaEvent_t ev_start = h->pipe_ev[2 * n_chunks];
+    CU(h, cudaEventRecord(ev_start, s)); // staging buffers (re)allocated, small arrays and counter reset queued
+    CU(h, cudaStreamWaitEvent(h->copy_stream, ev_start, 0));
+    CU(h, cudaStreamWaitEvent(h->aux_stream, ev_start, 0));
+    uint64_t copied = 0; // samples [0, copied) are on their way
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t f0 = c * CH, f1 = (f0 + CH < n_frames) ? f0 + CH : n_frames;
+        uint64_t hi = 0;
+        for (uint32_t f = f0; f < f1; f++) {
+            uint64_t e = lts1_index[f] + avail[f];
+            if (e > iq_samples) e = iq_samples;
+            if (e > hi) hi = e;
+        }
+        uint64_t lo = lts1_index[f0] < iq_samples ? lts1_index[f0] : iq_samples;
+        if (lo < copied) lo = copied;
+        if (hi > lo) {
+            CU(h, cudaMemcpyAsync(h->d_iq + 2 * lo, iq + 2 * lo, (size_t)(hi - lo) * 2 * sizeof(double),
+                                  cudaMemcpyHostToDevice, h->copy_stream));
+            copied = hi;
+        }
+        cudaEvent_t ev_in = h->pipe_ev[2 * c], ev_out = h->pipe_ev[2 * c + 1];
+        CU(h, cudaEventRecord(ev_in, h->copy_stream));
+        cudaStream_t cs = (c & 1) ? h->aux_stream : s;
+        CU(h, cudaStreamWaitEvent(cs, ev_in, 0));
+        int rc = launch_range(h, cs, f0, f1 - f0, h->d_iq, iq_samples, h->d_lts1, h->d_avail, o, nullptr, nullptr);
+        if (rc != B200RX_OK) return rc;
+        CU(h, cudaEventRecord(ev_out, cs));
+        CU(h, cudaStreamWaitEvent(h->d2h_stream, ev_out, 0));
+        const uint32_t nf = f1 - f0;
+        if (payload_out)
+            CU(h, cudaMemcpyAsync(payload_out + (size_t)f0 * payload_stride, h->d_payload + (size_t)f0 * payload_stride,
+                                  (size_t)nf * payload_stride, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (payload_len) CU(h, cudaMemcpyAsync(payload_len + f0, h->d_len + f0, nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (rate_out) CU(h, cudaMemcpyAsync(rate_out + f0, h->d_rate + f0, nf, cudaMemcpyDeviceToHost, h->d2h_stream));
+        CU(h, cudaMemcpyAsync(status + f0, h->d_status + f0, nf, cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
+    CU(h, cudaStreamSynchronize(h->d2h_stream));
+    CU(h, cudaStreamSynchronize(h->aux_stream));
     CU(h, cudaStreamSynchronize(s));
     return B200RX_OK;
 }

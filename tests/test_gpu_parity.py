@@ -242,6 +242,10 @@ def test_config2_full_batch_properties_and_sampled_parity(rx_factory):
     assert set(np.unique(a["status"])) <= {0, 3}
     assert np.all(a["length"] == 1500) and np.all(a["rate"] == 10)
     assert np.array_equal(a["payload"][ok], payloads[ok])
+    # the host-buffer entry point (chunked H2D / decode / D2H pipeline above 512 frames) must agree
+    hp, hl, hr, hs = rx.decode_batch(c["iq"], c["lts1"], c["avail"])
+    assert np.array_equal(hs, a["status"]) and np.array_equal(hp, a["payload"])
+    assert np.array_equal(hl.astype(int), a["length"]) and np.array_equal(hr, a["rate"])
     checker = _checker()
     idx = np.concatenate([np.arange(96), np.nonzero(~ok)[0][:32], rng.integers(0, n, 64)])
     for f in idx:
