@@ -10,6 +10,8 @@
 #include "viterbi_core.cuh"
 #include "viterbi_acs2.cuh"
 
+#include <stdlib.h>
+
 namespace b200rx {
 
 namespace {
@@ -50,31 +52,20 @@ __global__ void bm_from_symbols_kernel(const uint8_t *symbols, uint64_t symbols_
 // Per 24 steps and frame: one 96 B read of metric words (staged through shared memory, double
 // buffered, prefetched one block ahead) and three 64 B survivor stores.
 // ------------------------------------------------------------------------------------------------
-constexpr int ACS2_WARPS = 2;
-
-template <int PH>
-__device__ __forceinline__ void acs2_one(uint32_t (&R)[ACS2_NR], uint32_t &acc0, uint32_t &acc1, uint32_t w,
-                                         const Acs2Lane &L, int glane, int group)
+template <int LB>
+__global__ void __launch_bounds__(64) viterbi_acs2_kernel(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride,
+                                                          uint32_t *dec, uint32_t dec_stride_words, uint32_t n_frames,
+                                                          uint32_t neg1)
 {
-    uint32_t D[ACS2_NR];
-    acs2_step<PH>(R, D, w, L);
-    // bytes 1 and 3 of each raw decision word are 0/1: gather 4 of them, shift into the 8-step history
-    acc0 = acc0 * 2u + __byte_perm(D[0], D[1], 0x7531u);
-    acc1 = acc1 * 2u + __byte_perm(D[2], D[3], 0x7531u);
-    acs2_renorm(R, glane, group);
-}
-
-__global__ void __launch_bounds__(ACS2_WARPS * 32) viterbi_acs2_kernel(const FrameDesc *desc, const uint32_t *bm,
-                                                                        uint32_t bm_stride, uint32_t *dec,
-                                                                        uint32_t dec_stride_words, uint32_t n_frames,
-                                                                        uint32_t neg1)
-{
-    static_assert(ACS2_NR == 4, "decision packing below assumes 4 registers per lane");
-    __shared__ __align__(16) uint32_t s_w[ACS2_WARPS][2][ACS2_FPW][ACS2_BLK];
+    using A = Acs2<LB>;
+    constexpr int WARPS = 2, T = A::T, NR = A::NR, FPW = A::FPW;
+    constexpr int LOADERS = 6;             // 16-byte pieces per 24 metric words
+    constexpr int PER_LANE = (LOADERS + T - 1) / T; // pieces each lane of a group moves (T = 4: 2, else 1)
+    __shared__ __align__(16) uint32_t s_w[WARPS][2][FPW][ACS2_BLK];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int group = lane >> ACS2_LB, glane = lane & (ACS2_T - 1);
-    const uint32_t frame0 = (blockIdx.x * ACS2_WARPS + warp) * ACS2_FPW;
+    const int group = lane >> LB, glane = lane & (T - 1);
+    const uint32_t frame0 = (blockIdx.x * WARPS + warp) * FPW;
     if (frame0 >= n_frames) return;
     const uint32_t frame = min(frame0 + group, n_frames - 1); // surplus groups shadow the last frame (no stores)
     const bool live = frame0 + group < n_frames;
@@ -86,47 +77,67 @@ __global__ void __launch_bounds__(ACS2_WARPS * 32) viterbi_acs2_kernel(const Fra
     const uint32_t *w_in = bm + (size_t)frame * bm_stride;
     uint32_t *d_out = dec + (size_t)frame * dec_stride_words;
 
-    Acs2Lane L;
-    acs2_lane_init(L, glane, neg1);
-    uint32_t R[ACS2_NR];
-#pragma unroll
-    for (int i = 0; i < ACS2_NR; i++) R[i] = 0x003F003Fu;
-    if (glane == 0) R[0] = 0x0000003Fu; // state 0 (high half of register 0) starts at 0 (viterbi.cpp:71-78)
+    typename A::Lane L;
+    A::lane_init(L, glane, neg1);
+    uint32_t R[NR];
+    A::init_metrics(R, glane);
 
-    // lanes 0..5 of each group move the group's 24 metric words (6 x 16 B) per block
-    uint4 pre = make_uint4(0, 0, 0, 0);
-    if (glane < 6) pre = __ldg(reinterpret_cast<const uint4 *>(w_in) + glane);
+    // the lanes of each group move the group's 24 metric words (6 x 16 B) per block
+    uint4 pre[PER_LANE];
+#pragma unroll
+    for (int j = 0; j < PER_LANE; j++) {
+        const int piece = glane * PER_LANE + j;
+        pre[j] = make_uint4(0, 0, 0, 0);
+        if (piece < LOADERS) pre[j] = __ldg(reinterpret_cast<const uint4 *>(w_in) + piece);
+    }
     for (uint32_t b = 0; b < n_blocks; b++) {
         uint32_t *sw = &s_w[warp][b & 1][group][0];
-        if (glane < 6) reinterpret_cast<uint4 *>(sw)[glane] = pre;
+#pragma unroll
+        for (int j = 0; j < PER_LANE; j++) {
+            const int piece = glane * PER_LANE + j;
+            if (piece < LOADERS) reinterpret_cast<uint4 *>(sw)[piece] = pre[j];
+        }
         __syncwarp();
-        if (glane < 6 && b + 1 < n_blocks && (b + 1) < my_blocks + 0u)
-            pre = __ldg(reinterpret_cast<const uint4 *>(w_in + (size_t)(b + 1) * ACS2_BLK) + glane);
-        uint32_t *d_blk = d_out + (size_t)b * 3 * ACS2_WORDS_PER_8 + glane * 2;
+        if (b + 1 < my_blocks) {
+#pragma unroll
+            for (int j = 0; j < PER_LANE; j++) {
+                const int piece = glane * PER_LANE + j;
+                if (piece < LOADERS)
+                    pre[j] = __ldg(reinterpret_cast<const uint4 *>(w_in + (size_t)(b + 1) * ACS2_BLK) + piece);
+            }
+        }
+        uint32_t *d_blk = d_out + (size_t)b * 3 * ACS2_WORDS_PER_8 + glane * (NR / 2);
         const bool store = b < my_blocks;
 #pragma unroll
         for (int o = 0; o < 3; o++) {
             const uint4 wa = reinterpret_cast<const uint4 *>(sw)[2 * o];
             const uint4 wb = reinterpret_cast<const uint4 *>(sw)[2 * o + 1];
-            uint32_t acc0 = 0, acc1 = 0;
+            uint32_t acc[NR / 2];
+#pragma unroll
+            for (int j = 0; j < NR / 2; j++) acc[j] = 0;
             // 8 steps; phase = (8 * o + i) % 6
             if (o == 0) {
-                acs2_one<0>(R, acc0, acc1, wa.x, L, glane, group); acs2_one<1>(R, acc0, acc1, wa.y, L, glane, group);
-                acs2_one<2>(R, acc0, acc1, wa.z, L, glane, group); acs2_one<3>(R, acc0, acc1, wa.w, L, glane, group);
-                acs2_one<4>(R, acc0, acc1, wb.x, L, glane, group); acs2_one<5>(R, acc0, acc1, wb.y, L, glane, group);
-                acs2_one<0>(R, acc0, acc1, wb.z, L, glane, group); acs2_one<1>(R, acc0, acc1, wb.w, L, glane, group);
+                A::template one<0>(R, acc, wa.x, L, glane, group); A::template one<1>(R, acc, wa.y, L, glane, group);
+                A::template one<2>(R, acc, wa.z, L, glane, group); A::template one<3>(R, acc, wa.w, L, glane, group);
+                A::template one<4>(R, acc, wb.x, L, glane, group); A::template one<5>(R, acc, wb.y, L, glane, group);
+                A::template one<0>(R, acc, wb.z, L, glane, group); A::template one<1>(R, acc, wb.w, L, glane, group);
             } else if (o == 1) {
-                acs2_one<2>(R, acc0, acc1, wa.x, L, glane, group); acs2_one<3>(R, acc0, acc1, wa.y, L, glane, group);
-                acs2_one<4>(R, acc0, acc1, wa.z, L, glane, group); acs2_one<5>(R, acc0, acc1, wa.w, L, glane, group);
-                acs2_one<0>(R, acc0, acc1, wb.x, L, glane, group); acs2_one<1>(R, acc0, acc1, wb.y, L, glane, group);
-                acs2_one<2>(R, acc0, acc1, wb.z, L, glane, group); acs2_one<3>(R, acc0, acc1, wb.w, L, glane, group);
+                A::template one<2>(R, acc, wa.x, L, glane, group); A::template one<3>(R, acc, wa.y, L, glane, group);
+                A::template one<4>(R, acc, wa.z, L, glane, group); A::template one<5>(R, acc, wa.w, L, glane, group);
+                A::template one<0>(R, acc, wb.x, L, glane, group); A::template one<1>(R, acc, wb.y, L, glane, group);
+                A::template one<2>(R, acc, wb.z, L, glane, group); A::template one<3>(R, acc, wb.w, L, glane, group);
             } else {
-                acs2_one<4>(R, acc0, acc1, wa.x, L, glane, group); acs2_one<5>(R, acc0, acc1, wa.y, L, glane, group);
-                acs2_one<0>(R, acc0, acc1, wa.z, L, glane, group); acs2_one<1>(R, acc0, acc1, wa.w, L, glane, group);
-                acs2_one<2>(R, acc0, acc1, wb.x, L, glane, group); acs2_one<3>(R, acc0, acc1, wb.y, L, glane, group);
-                acs2_one<4>(R, acc0, acc1, wb.z, L, glane, group); acs2_one<5>(R, acc0, acc1, wb.w, L, glane, group);
+                A::template one<4>(R, acc, wa.x, L, glane, group); A::template one<5>(R, acc, wa.y, L, glane, group);
+                A::template one<0>(R, acc, wa.z, L, glane, group); A::template one<1>(R, acc, wa.w, L, glane, group);
+                A::template one<2>(R, acc, wb.x, L, glane, group); A::template one<3>(R, acc, wb.y, L, glane, group);
+                A::template one<4>(R, acc, wb.z, L, glane, group); A::template one<5>(R, acc, wb.w, L, glane, group);
             }
-            if (store) *reinterpret_cast<uint2 *>(d_blk + o * ACS2_WORDS_PER_8) = make_uint2(acc0, acc1);
+            if (store) {
+                uint32_t *dst = d_blk + o * ACS2_WORDS_PER_8;
+                if constexpr (NR / 2 == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                else if constexpr (NR / 2 == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(acc[0], acc[1]);
+                else dst[0] = acc[0];
+            }
         }
         __syncwarp();
     }
@@ -441,9 +452,25 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
                                uint32_t dec_stride_words, uint32_t n_frames, cudaStream_t s)
 {
     if (n_frames == 0) return cudaSuccess;
-    const uint32_t per_cta = ACS2_WARPS * ACS2_FPW;
-    viterbi_acs2_kernel<<<(n_frames + per_cta - 1) / per_cta, ACS2_WARPS * 32, 0, s>>>(desc, bm, bm_stride, dec,
-                                                                                         dec_stride_words, n_frames, 0xFFFFFFFFu);
+    // Lanes per frame (measured on B200, 4096 frames x 12 096 steps: 4 lanes 1.19 ms, 8 lanes 0.98 ms, 16 lanes
+    // 1.07 ms): 8 by default, 16 when the batch is too small to give every scheduler (4 per SM) a warp.
+    static int n_sm = 0, forced = -1;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+        const char *e = getenv("B200RX_ACS_LB");
+        forced = e ? atoi(e) : 0;
+    }
+    const uint32_t sched = 4u * (uint32_t)n_sm;
+    int lb = (n_frames * 8u >= 32u * sched * 3u / 4u) ? 3 : 4;
+    if (forced >= 2 && forced <= 4) lb = forced;
+    const uint32_t per_cta = 2u * (32u >> lb);
+    const uint32_t grid = (n_frames + per_cta - 1) / per_cta;
+    if (lb == 2) viterbi_acs2_kernel<2><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu);
+    else if (lb == 3) viterbi_acs2_kernel<3><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu);
+    else viterbi_acs2_kernel<4><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu);
     return cudaGetLastError();
 }
 
