@@ -25,6 +25,13 @@ namespace b200rx {
 namespace {
 
 constexpr int FE_WARPS = 8;
+constexpr int SOFT_STRIDE = 292;   // 288 soft bits + the erasure sentinel, padded to a multiple of 4
+constexpr int ERASURE_AT = 288;
+
+// Per rate: for trellis step t of an OFDM symbol the two soft-bit indices (demodulator order) it consumes,
+// i.e. depuncture (puncturer.cpp:94-118) composed with deinterleave (interleaver.cpp:31-37); ERASURE_AT marks a
+// re-inserted erasure (value 127).  Filled by upload_frontend_tables from step_index_pair() below.
+__constant__ uint32_t c_step_idx[11][216];
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 __constant__ double2 c_twiddle[64];  // exp(-2 pi i k / 64)
@@ -114,6 +121,29 @@ __device__ __forceinline__ uint32_t deint_at(const uint8_t *soft, int k)
     return soft[blk + 3 * (kk & 15) + (kk >> 4)];
 }
 
+__host__ __device__ inline uint32_t deint_index(int k)
+{
+    const int blk = (k / 48) * 48, kk = k - blk;
+    return (uint32_t)(blk + 3 * (kk & 15) + (kk >> 4));
+}
+
+// (i0 | i1 << 16) for trellis step t under puncturing mode punc
+__host__ __device__ inline uint32_t step_index_pair(int punc, int t)
+{
+    uint32_t i0, i1;
+    if (punc == PUNC_1_2) { i0 = deint_index(2 * t); i1 = deint_index(2 * t + 1); }
+    else if (punc == PUNC_3_4) {
+        const int g = t / 3, r = t - 3 * g;
+        if (r == 0) { i0 = deint_index(4 * g); i1 = deint_index(4 * g + 1); }
+        else { i0 = ERASURE_AT; i1 = deint_index(4 * g + 1 + r); }
+    } else {
+        const int g = t >> 1;
+        if ((t & 1) == 0) { i0 = deint_index(3 * g); i1 = ERASURE_AT; }
+        else { i0 = deint_index(3 * g + 1); i1 = deint_index(3 * g + 2); }
+    }
+    return i0 | (i1 << 16);
+}
+
 // The two depunctured soft symbols of trellis step t (0-based within the OFDM symbol), puncturer.cpp:94-118
 __device__ __forceinline__ void step_symbols(const uint8_t *soft, int punc, int t, uint32_t &s0, uint32_t &s1)
 {
@@ -162,8 +192,9 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const doubl
         e.y += rec.y * ref / 4.0;
     }
     // phase_tracker.cpp:92-98 rotates by exp(-i arg(e)) = conj(e) / |e|
-    const double mag = hypot(e.x, e.y);
-    const double2 rot = (mag > 0.0) ? make_double2(e.x / mag, -e.y / mag) : make_double2(1.0, 0.0);
+    const double m2 = e.x * e.x + e.y * e.y;
+    const double inv = rsqrt(m2); // 1 / |e|
+    const double2 rot = (m2 > 0.0) ? make_double2(e.x * inv, -e.y * inv) : make_double2(1.0, 0.0);
 
     const double scale = demap_scale(bpsc);
 #pragma unroll
@@ -190,7 +221,8 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     __shared__ double2 s_tw[64];
     __shared__ double2 s_hinv[64];
     __shared__ double2 s_xs[FE_WARPS][64];
-    __shared__ uint8_t s_soft[FE_WARPS][288];
+    __shared__ uint8_t s_soft[FE_WARPS][SOFT_STRIDE]; // [288] = 127: the erasure the index table points at
+    __shared__ uint32_t s_idx[216];                   // soft-bit indices (i0 | i1 << 16) of each trellis step of a symbol
     __shared__ uint32_t s_hdr_bm[32];
     __shared__ FrameDesc s_desc;
 
@@ -203,6 +235,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     const double2 *win = a.iq + p;
 
     if (tid < 64) s_tw[tid] = c_twiddle[tid];
+    if (tid < FE_WARPS) s_soft[tid][ERASURE_AT] = 127;
     if (tid == 0) {
         s_desc.n_steps = 0; s_desc.data_bits = 0; s_desc.field = 0; s_desc.length = 0;
         s_desc.rate = B200RX_RATE_INVALID; s_desc.status = B200RX_ST_TRUNCATED;
@@ -279,17 +312,20 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 
     // ---- data symbols ----
     const RateRow rr = rate_row(d.rate);
+    for (int t = tid; t < rr.dbps; t += FE_WARPS * 32) s_idx[t] = c_step_idx[d.rate][t];
+    __syncthreads();
     const uint32_t nsym = d.n_steps / rr.dbps;
     uint32_t *bm_out = a.bm + (size_t)frame * a.bm_stride;
     for (uint32_t s = warp; s < nsym; s += FE_WARPS) {
         double2 *dbg = nullptr;
         if (a.dbg_eq && s + 1 < a.dbg_eq_vectors) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors + s + 1) * 48;
         process_symbol(ctx, win + 128 + 80 * (size_t)(s + 1) + 16, (int)(s + 1), rr.bpsc, lane, dbg);
+        uint32_t *sym_out = bm_out + (size_t)s * rr.dbps;
         for (int t = lane; t < rr.dbps; t += 32) {
-            uint32_t s0, s1;
-            step_symbols(ctx.soft, rr.punc, t, s0, s1);
+            const uint32_t pair = s_idx[t];
+            const uint32_t s0 = ctx.soft[pair & 0xFFFFu], s1 = ctx.soft[pair >> 16];
             const size_t step = (size_t)s * rr.dbps + t;
-            bm_out[step] = bm_word(s0, s1);
+            sym_out[t] = bm_word(s0, s1);
             if (a.dbg_depunct && 2 * step + 1 < a.dbg_depunct_stride) {
                 uint8_t *dp = a.dbg_depunct + (size_t)frame * a.dbg_depunct_stride + 2 * step;
                 dp[0] = (uint8_t)s0; dp[1] = (uint8_t)s1;
@@ -303,7 +339,14 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 
 cudaError_t upload_frontend_tables(const double2 *tw, const int8_t *pol)
 {
-    cudaError_t e = cudaMemcpyToSymbol(c_twiddle, tw, sizeof(double2) * 64);
+    static uint32_t idx[11][216];
+    for (int r = 0; r < 11; r++) {
+        const RateRow rr = rate_row(r);
+        for (int t = 0; t < 216; t++) idx[r][t] = t < rr.dbps ? step_index_pair(rr.punc, t) : (ERASURE_AT | (ERASURE_AT << 16));
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_step_idx, idx, sizeof(idx));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_twiddle, tw, sizeof(double2) * 64);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_polarity, pol, 127);
 }
