@@ -237,12 +237,6 @@ __device__ __forceinline__ uint32_t tb_walk_global(const uint32_t *dec, uint32_t
     return tb_pos_to_state(q, n_to + 6);
 }
 
-__device__ __forceinline__ void tb_cp_async16(uint32_t *smem_dst, const uint32_t *gsrc)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
-}
-
 // a(x) * b(x) mod P(x) in the reflected CRC-32 representation (bit 31 = x^0)
 __device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
 {
@@ -262,8 +256,10 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
     __shared__ uint8_t s_entry[TB_MAX_TILES + 1], s_exit[TB_MAX_TILES + 1];
     __shared__ uint32_t s_crc[4][256];
     __shared__ uint32_t s_flag;
+    __shared__ short s_mtop[TB_THREADS];
 
     const int tid = threadIdx.x;
+    const uint32_t s_rows_u32 = (uint32_t)__cvta_generic_to_shared(s_rows);
     if (!a.raw_mode)
         for (int i = tid; i < 1024; i += TB_THREADS) (&s_crc[0][0])[i] = (&c_crc_tab[0][0])[i];
 
@@ -304,21 +300,27 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
                     if (n < hi && (n & 7) == 0) s_bytes[n >> 3] = (uint8_t)e;
                 }
             }
+            // Each warp stages and walks its own 32 tiles; warps drift apart, so one warp's wait for its rows
+            // is covered by the other warps' walking (no CTA-wide barrier inside the rounds).
+            // Lane l moves piece (l & 15) of tiles (l >> 4), (l >> 4) + 2, ... : 16 cp.async of 16 B per round.
+            const int wtile0 = tid & ~31, lane = tid & 31;
+            s_mtop[tid] = active ? (short)((n + 1) / 24 - 1) : (short)-1; // first block of my tile (n + 1 is a multiple of 24 now)
+            __syncwarp();
+            const int part = lane & 15;
+            const uint32_t dst0 = s_rows_u32 + (uint32_t)((wtile0 + (lane >> 4)) * TB_TILE_W + (part >> 2) * TB_ROW_W + (part & 3) * 4) * 4u;
+            const uint32_t *src0 = dec + part * 4;
             for (int round = 0; round < TB_ROUNDS; round++) {
-                __syncthreads(); // everybody is done with the rows of the previous round
-                // stage rows 3m .. 3m+3 of every tile's next block m: 16 pieces of 16 B per tile
-                for (int i = tid; i < TB_THREADS * 16; i += TB_THREADS) {
-                    const int tile = i >> 4, part = i & 15;
-                    const int tk = g * TB_THREADS + tile;
-                    const int tlo = tk * TB_TILE;
-                    const int tfrom = min(min(tlo + TB_TILE, nbits) + TB_PRE, nbits);
-                    const int tm = tfrom / 24 - 1 - round; // block index this tile walks in this round
-                    if (tk < ntiles && tm * 24 >= tlo)
-                        tb_cp_async16(s_rows + tile * TB_TILE_W + (part >> 2) * TB_ROW_W + (part & 3) * 4,
-                                      dec + (size_t)(3 * tm) * ACS2_WORDS_PER_8 + part * 4);
+                __syncwarp(); // the warp is done with the rows of the previous round
+#pragma unroll 4
+                for (int j = 0; j < 16; j++) {
+                    const int tile = wtile0 + (lane >> 4) + 2 * j;
+                    const int m = (int)s_mtop[tile] - round;          // block this tile walks in this round
+                    if (m >= 4 * (g * TB_THREADS + tile))              // still inside [lo, from): lo / 24 = 4 k
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(2 * j * TB_TILE_W * 4)),
+                                     "l"(src0 + (size_t)(3 * m) * ACS2_WORDS_PER_8));
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
-                __syncthreads();
+                __syncwarp();
                 if (active && n >= lo) {
                     if (n == hi - 1) entry = tb_pos_to_state(q, n + 7);
                     const int m3 = (n - 23) >> 3;
