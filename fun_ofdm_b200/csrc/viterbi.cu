@@ -337,24 +337,32 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
         }
         __syncthreads();
 
-        // verify the chain in parallel; only if some tile had not merged, repair serially from the top
-        int bad = 0;
-        for (int k = tid; k < ntiles - 1; k += TB_THREADS) bad |= (s_entry[k] != s_exit[k + 1]);
-        if (__syncthreads_or(bad)) {
-            if (tid == 0) {
-                unsigned rewalks = 0;
-                for (int k = ntiles - 2; k >= 0; k--) {
-                    if (s_entry[k] != s_exit[k + 1]) {
-                        const int lo = k * TB_TILE, hi = lo + TB_TILE;
-                        s_exit[k] = (uint8_t)tb_walk_global(dec, (uint32_t)s_exit[k + 1], hi, lo, s_bytes);
-                        s_entry[k] = s_exit[k + 1];
-                        rewalks++;
-                    }
-                }
-                if (a.counters) atomicAdd(&a.counters[4], (unsigned long long)rewalks);
+        // Verify the chain in parallel.  A tile whose entry state differs from the exit state of the tile above
+        // had not merged within its pre-roll: it is re-walked from that exit state.  All such tiles are repaired
+        // at once and the check repeated (a repaired tile may end in a different state than before and invalidate
+        // the tile below it); exactness spreads downwards from the top tile at least one tile per pass, in
+        // practice one or two passes suffice even for frames that are pure noise.
+        unsigned rewalks = 0;
+        for (int pass = 0; pass < ntiles; pass++) {
+            uint32_t fix_from[(TB_MAX_TILES + TB_THREADS - 1) / TB_THREADS];
+            int bad = 0, j = 0;
+            for (int k = tid; k < ntiles - 1; k += TB_THREADS, j++) {
+                const uint32_t above = s_exit[k + 1];
+                fix_from[j] = (s_entry[k] != above) ? above : 0xFFu;
+                bad |= (fix_from[j] != 0xFFu);
+            }
+            if (!__syncthreads_or(bad)) break; // (also orders the reads above before the writes below)
+            j = 0;
+            for (int k = tid; k < ntiles - 1; k += TB_THREADS, j++) {
+                if (fix_from[j] == 0xFFu) continue;
+                const int lo = k * TB_TILE, hi = lo + TB_TILE;
+                s_exit[k] = (uint8_t)tb_walk_global(dec, fix_from[j], hi, lo, s_bytes);
+                s_entry[k] = (uint8_t)fix_from[j];
+                rewalks++;
             }
             __syncthreads();
         }
+        if (rewalks && a.counters) atomicAdd(&a.counters[4], (unsigned long long)rewalks);
 
         if (a.dbg_decoded)
             for (int i = tid; i < nbytes && i < (int)a.dbg_decoded_stride; i += TB_THREADS)
