@@ -43,6 +43,17 @@ struct b200rx_handle {
     uint8_t *d_rate = nullptr;
     uint8_t *d_status = nullptr;
 
+    // pipeline depth > 1: consecutive device-buffer calls rotate over `depth` lanes (own scratch set, own stream),
+    // so that batch j+1 starts while batch j is still in its Viterbi kernel (b200rx_set_pipeline_depth)
+    struct Lane {
+        FrameDesc *desc = nullptr; uint32_t *bm = nullptr; uint32_t *dec = nullptr; unsigned long long *counters = nullptr;
+        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; bool used = false;
+    };
+    Lane lanes[3];
+    uint32_t depth = 1;
+    uint64_t call_idx = 0;
+    cudaEvent_t ev_in = nullptr;
+
     // host-buffer pipeline: H2D of chunk i+1 overlaps the kernels of chunk i
     cudaStream_t copy_stream = nullptr, aux_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> pipe_ev; // 2 per chunk: samples landed, results ready
@@ -67,6 +78,12 @@ inline cudaEvent_t *call_events(b200rx_handle *h)
 {
     if (h->ring_slots && h->ring_used < h->ring_slots) return &h->ring[4 * (size_t)(h->ring_used++)];
     return h->ev;
+}
+
+// scratch set 0 is the one every non-pipelined entry point uses
+inline void use_lane(b200rx_handle *h, int i)
+{
+    h->desc = h->lanes[i].desc; h->bm = h->lanes[i].bm; h->dec = h->lanes[i].dec; h->counters = h->lanes[i].counters;
 }
 
 #define CU(h, call)                                                         \
@@ -215,6 +232,7 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
         return code;
     }
     h->stream = h->own_stream;
+    h->lanes[0].desc = h->desc; h->lanes[0].bm = h->bm; h->lanes[0].dec = h->dec; h->lanes[0].counters = h->counters;
     *out = h;
     return B200RX_OK;
 }
@@ -223,7 +241,15 @@ int b200rx_destroy(b200rx_handle *h)
 {
     if (!h) return B200RX_OK;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream && h->desc) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 3; i++) {
+        b200rx_handle::Lane &l = h->lanes[i];
+        if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
+        if (l.done) cudaEventDestroy(l.done);
+        if (i > 0) { cudaFree(l.desc); cudaFree(l.bm); cudaFree(l.dec); cudaFree(l.counters); }
+    }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    use_lane(h, 0);
     cudaFree(h->desc); cudaFree(h->bm); cudaFree(h->dec); cudaFree(h->counters);
     cudaFree(h->d_iq); cudaFree(h->d_lts1); cudaFree(h->d_avail); cudaFree(h->d_payload);
     cudaFree(h->d_len); cudaFree(h->d_rate); cudaFree(h->d_status);
@@ -249,7 +275,55 @@ int b200rx_synchronize(b200rx_handle *h)
 {
     if (!h) return B200RX_E_ARG;
     CU(h, cudaSetDevice(h->device));
+    for (int i = 0; i < 3; i++)
+        if (h->lanes[i].stream && h->lanes[i].used) CU(h, cudaStreamSynchronize(h->lanes[i].stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return B200RX_OK;
+}
+
+int b200rx_set_pipeline_depth(b200rx_handle *h, uint32_t depth)
+{
+    if (!h || depth < 1 || depth > 3) return fail(h, B200RX_E_ARG, "b200rx_set_pipeline_depth: depth must be 1, 2 or 3");
+    int rc = b200rx_synchronize(h);
+    if (rc != B200RX_OK) return rc;
+    const size_t nf = h->limits.max_frames;
+    for (uint32_t i = 0; i < depth; i++) {
+        b200rx_handle::Lane &l = h->lanes[i];
+        if (depth > 1 && !l.stream) {
+            CU(h, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+            CU(h, cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        }
+        if (i > 0 && !l.desc) {
+            cudaError_t e = cudaMalloc((void **)&l.desc, nf * sizeof(FrameDesc));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&l.bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&l.dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&l.counters, 8 * sizeof(unsigned long long));
+            if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_set_pipeline_depth: scratch for an extra lane", e);
+        }
+    }
+    if (!h->ev_in) CU(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    h->depth = depth;
+    h->call_idx = 0;
+    use_lane(h, 0);
+    return B200RX_OK;
+}
+
+int b200rx_join(b200rx_handle *h, uint32_t calls_back)
+{
+    if (!h) return B200RX_E_ARG;
+    if (h->depth <= 1) return B200RX_OK; // everything already runs in order on the caller's stream
+    if (calls_back >= h->depth) return fail(h, B200RX_E_ARG, "b200rx_join: calls_back must be < pipeline depth");
+    if (h->call_idx < (uint64_t)calls_back + 1) return B200RX_OK;
+    CU(h, cudaSetDevice(h->device));
+    if (calls_back == 0) {
+        // everything issued so far
+        for (uint32_t i = 0; i < h->depth; i++)
+            if (h->lanes[i].used) CU(h, cudaStreamWaitEvent(h->stream, h->lanes[i].done, 0));
+    } else {
+        // exactly the call issued calls_back calls before the latest one (its lane has not been reused yet)
+        const uint64_t c = h->call_idx - 1 - calls_back;
+        CU(h, cudaStreamWaitEvent(h->stream, h->lanes[c % h->depth].done, 0));
+    }
     return B200RX_OK;
 }
 
@@ -348,6 +422,14 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
     if (n_frames == 0) return B200RX_OK;
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
+    b200rx_handle::Lane *lane = nullptr;
+    if (h->depth > 1) {
+        lane = &h->lanes[h->call_idx % h->depth];
+        CU(h, cudaEventRecord(h->ev_in, h->stream)); // the caller's inputs are ready at this point of its stream
+        CU(h, cudaStreamWaitEvent(lane->stream, h->ev_in, 0));
+        s = lane->stream;
+        use_lane(h, (int)(h->call_idx % h->depth));
+    }
 
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     cudaEvent_t *ev = call_events(h);
@@ -355,6 +437,11 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
     int rc = launch_range(h, s, 0, n_frames, iq_dev, iq_samples, lts1_index_dev, avail_dev, o, dbg, ev);
     if (rc != B200RX_OK) return rc;
     if (ev == h->ev) h->ev_valid = true;
+    if (lane) {
+        CU(h, cudaEventRecord(lane->done, s));
+        lane->used = true;
+    }
+    h->call_idx++;
     return B200RX_OK;
 }
 
@@ -367,6 +454,11 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
     if (!iq || !lts1_index || !avail || !status) return fail(h, B200RX_E_ARG, "b200rx_decode_batch: null argument");
     if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_batch: n_frames exceeds max_frames");
     if (n_frames == 0) return B200RX_OK;
+    if (h->depth > 1) { // these entry points are not pipelined: drain the lanes, work on scratch set 0
+        int rcq = b200rx_synchronize(h);
+        if (rcq != B200RX_OK) return rcq;
+        use_lane(h, 0);
+    }
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
 
@@ -462,6 +554,11 @@ int b200rx_decode_headers(b200rx_handle *h, const double *iq, uint64_t iq_sample
     if (!iq || !lts1_index || !avail || !status) return fail(h, B200RX_E_ARG, "b200rx_decode_headers: null argument");
     if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_headers: n_frames exceeds max_frames");
     if (n_frames == 0) return B200RX_OK;
+    if (h->depth > 1) { // these entry points are not pipelined: drain the lanes, work on scratch set 0
+        int rcq = b200rx_synchronize(h);
+        if (rcq != B200RX_OK) return rcq;
+        use_lane(h, 0);
+    }
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const size_t iq_bytes = (size_t)iq_samples * 2 * sizeof(double);
@@ -506,6 +603,11 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
     if (max_data_bits + 6 > h->max_steps) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: trellis longer than the handle's capacity");
     if ((symbols_stride & 1) || ((uintptr_t)symbols_dev & 1)) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: symbols must be 2-byte aligned");
     if (n_frames == 0) return B200RX_OK;
+    if (h->depth > 1) { // these entry points are not pipelined: drain the lanes, work on scratch set 0
+        int rcq = b200rx_synchronize(h);
+        if (rcq != B200RX_OK) return rcq;
+        use_lane(h, 0);
+    }
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
@@ -547,7 +649,7 @@ int b200rx_profile_read(b200rx_handle *h, uint32_t *calls, float *frontend_ms, f
 {
     if (!h || !calls || !frontend_ms || !viterbi_ms || !traceback_ms) return B200RX_E_ARG;
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaStreamSynchronize(h->stream));
+    { int rcq = b200rx_synchronize(h); if (rcq != B200RX_OK) return rcq; }
     *calls = h->ring_used;
     *frontend_ms = *viterbi_ms = *traceback_ms = 0.f;
     for (uint32_t i = 0; i < h->ring_used; i++) {
@@ -568,7 +670,7 @@ int b200rx_get_stats(b200rx_handle *h, b200rx_stats *out)
     memset(out, 0, sizeof(*out));
     if (!h->ev_valid) return B200RX_OK;
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaStreamSynchronize(h->stream));
+    { int rcq = b200rx_synchronize(h); if (rcq != B200RX_OK) return rcq; }
     CU(h, cudaEventElapsedTime(&out->frontend_ms, h->ev[0], h->ev[1]));
     CU(h, cudaEventElapsedTime(&out->viterbi_ms, h->ev[1], h->ev[2]));
     CU(h, cudaEventElapsedTime(&out->traceback_ms, h->ev[2], h->ev[3]));

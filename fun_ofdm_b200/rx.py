@@ -79,6 +79,10 @@ def load_library():
     L.b200rx_set_stream.argtypes = [vp, vp]
     L.b200rx_synchronize.restype = C.c_int
     L.b200rx_synchronize.argtypes = [vp]
+    L.b200rx_set_pipeline_depth.restype = C.c_int
+    L.b200rx_set_pipeline_depth.argtypes = [vp, u32]
+    L.b200rx_join.restype = C.c_int
+    L.b200rx_join.argtypes = [vp, u32]
     L.b200rx_host_alloc.restype = C.c_int
     L.b200rx_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.b200rx_host_free.restype = C.c_int
@@ -150,6 +154,12 @@ class Receiver:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.b200rx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or None)), "b200rx_set_stream")
+
+    def set_pipeline_depth(self, depth):
+        self._check(self.lib.b200rx_set_pipeline_depth(self.h, int(depth)), "b200rx_set_pipeline_depth")
+
+    def join(self, calls_back=0):
+        self._check(self.lib.b200rx_join(self.h, int(calls_back)), "b200rx_join")
 
     def synchronize(self):
         self._check(self.lib.b200rx_synchronize(self.h), "b200rx_synchronize")

@@ -273,3 +273,40 @@ def test_worst_case_length(rx_factory):
     small = rx_factory(8, 100)
     g2 = gpu_decode(small, c, taps=False)
     assert np.all(g2["status"] == 5)
+
+
+def test_pipelined_calls_match_sequential(ref, rx_factory):
+    """b200rx_set_pipeline_depth(3): consecutive calls overlap on three lanes; every call must give exactly what
+    it gives alone, whatever runs next to it."""
+    rng = np.random.default_rng(77)
+    rx = rx_factory(64, 1500)
+    dev = torch.device("cuda:0")
+    corpora = []
+    for k in range(7):
+        n = int(rng.integers(5, 40))
+        rates = list(rng.integers(0, 11, n))
+        lengths = list(rng.integers(0, 1500, n))
+        corpora.append(make_corpus(ref, rng, rates, lengths, snr_db=[None, 30, 12][k % 3]))
+    seq = [gpu_decode(rx, c, taps=False) for c in corpora]
+    rx.set_pipeline_depth(3)
+    bufs = []
+    for c in corpora:
+        n = len(c["lts1"])
+        iq = torch.from_numpy(c["iq"].view(np.float64)).to(dev)
+        l = torch.from_numpy(c["lts1"]).to(dev)
+        a = torch.from_numpy(c["avail"]).to(dev)
+        o = (torch.zeros((n, 1500), dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.int16, device=dev),
+             torch.zeros(n, dtype=torch.uint8, device=dev), torch.full((n,), 99, dtype=torch.uint8, device=dev))
+        bufs.append((iq, l, a, o))
+    for iq, l, a, o in bufs:            # all seven issued without waiting
+        rx.decode_batch_dev(iq, l, a, *o)
+    rx.join(0)
+    rx.synchronize()
+    for (iq, l, a, o), s in zip(bufs, seq):
+        assert np.array_equal(o[3].cpu().numpy(), s["status"])
+        assert np.array_equal(o[0].cpu().numpy(), s["payload"])
+        assert np.array_equal(o[1].cpu().numpy().astype(np.uint16).astype(int), s["length"])
+        assert np.array_equal(o[2].cpu().numpy(), s["rate"])
+    rx.set_pipeline_depth(1)
+    again = gpu_decode(rx, corpora[0], taps=False)
+    assert np.array_equal(again["payload"], seq[0]["payload"]) and np.array_equal(again["status"], seq[0]["status"])
