@@ -308,9 +308,12 @@ int b200rx_set_pipeline_depth(b200rx_handle *h, uint32_t depth)
     return B200RX_OK;
 }
 
-int b200rx_join(b200rx_handle *h, uint32_t calls_back)
+int b200rx_join(b200rx_handle *h, uint32_t calls_back) { return b200rx_join_on(h, calls_back, h ? (void *)h->stream : nullptr); }
+
+int b200rx_join_on(b200rx_handle *h, uint32_t calls_back, void *cuda_stream)
 {
     if (!h) return B200RX_E_ARG;
+    cudaStream_t target = (cudaStream_t)cuda_stream;
     if (h->depth <= 1) return B200RX_OK; // everything already runs in order on the caller's stream
     if (calls_back >= h->depth) return fail(h, B200RX_E_ARG, "b200rx_join: calls_back must be < pipeline depth");
     if (h->call_idx < (uint64_t)calls_back + 1) return B200RX_OK;
@@ -318,11 +321,11 @@ int b200rx_join(b200rx_handle *h, uint32_t calls_back)
     if (calls_back == 0) {
         // everything issued so far
         for (uint32_t i = 0; i < h->depth; i++)
-            if (h->lanes[i].used) CU(h, cudaStreamWaitEvent(h->stream, h->lanes[i].done, 0));
+            if (h->lanes[i].used) CU(h, cudaStreamWaitEvent(target, h->lanes[i].done, 0));
     } else {
         // exactly the call issued calls_back calls before the latest one (its lane has not been reused yet)
         const uint64_t c = h->call_idx - 1 - calls_back;
-        CU(h, cudaStreamWaitEvent(h->stream, h->lanes[c % h->depth].done, 0));
+        CU(h, cudaStreamWaitEvent(target, h->lanes[c % h->depth].done, 0));
     }
     return B200RX_OK;
 }

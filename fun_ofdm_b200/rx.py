@@ -83,6 +83,8 @@ def load_library():
     L.b200rx_set_pipeline_depth.argtypes = [vp, u32]
     L.b200rx_join.restype = C.c_int
     L.b200rx_join.argtypes = [vp, u32]
+    L.b200rx_join_on.restype = C.c_int
+    L.b200rx_join_on.argtypes = [vp, u32, vp]
     L.b200rx_host_alloc.restype = C.c_int
     L.b200rx_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.b200rx_host_free.restype = C.c_int
@@ -160,6 +162,9 @@ class Receiver:
 
     def join(self, calls_back=0):
         self._check(self.lib.b200rx_join(self.h, int(calls_back)), "b200rx_join")
+
+    def join_on(self, calls_back, cuda_stream_ptr):
+        self._check(self.lib.b200rx_join_on(self.h, int(calls_back), C.c_void_p(cuda_stream_ptr)), "b200rx_join_on")
 
     def synchronize(self):
         self._check(self.lib.b200rx_synchronize(self.h), "b200rx_synchronize")

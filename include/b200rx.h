@@ -116,6 +116,9 @@ B200RX_API int b200rx_synchronize(b200rx_handle *h);
  * b200rx_synchronize() always waits for everything. */
 B200RX_API int b200rx_set_pipeline_depth(b200rx_handle *h, uint32_t depth);
 B200RX_API int b200rx_join(b200rx_handle *h, uint32_t calls_back);
+/* Same, but the waiting stream is `cuda_stream` (e.g. a communication stream that gathers a finished batch's
+ * status while the handle's stream keeps issuing new batches). */
+B200RX_API int b200rx_join_on(b200rx_handle *h, uint32_t calls_back, void *cuda_stream);
 
 /* Pinned host memory for the host-buffer entry point (plain malloc'ed memory also works, slower). */
 B200RX_API int b200rx_host_alloc(void **ptr, size_t bytes);
