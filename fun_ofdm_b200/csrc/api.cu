@@ -49,13 +49,13 @@ struct b200rx_handle {
         FrameDesc *desc = nullptr; uint32_t *bm = nullptr; uint32_t *dec = nullptr; unsigned long long *counters = nullptr;
         cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; bool used = false;
     };
-    Lane lanes[3];
+    Lane lanes[B200RX_MAX_PIPELINE_DEPTH];
     uint32_t depth = 1;
     uint64_t call_idx = 0;
     cudaEvent_t ev_in = nullptr;
 
     // host-buffer pipeline: H2D of chunk i+1 overlaps the kernels of chunk i
-    cudaStream_t copy_stream = nullptr, aux_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, aux_stream[3] = {nullptr, nullptr, nullptr}, d2h_stream = nullptr;
     std::vector<cudaEvent_t> pipe_ev; // 2 per chunk: samples landed, results ready
 
     uint64_t launches = 0;
@@ -213,7 +213,8 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 3; i++)
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
     A((void **)&h->desc, nf * sizeof(FrameDesc));
@@ -242,7 +243,7 @@ int b200rx_destroy(b200rx_handle *h)
     if (!h) return B200RX_OK;
     cudaSetDevice(h->device);
     if (h->stream && h->desc) cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < B200RX_MAX_PIPELINE_DEPTH; i++) {
         b200rx_handle::Lane &l = h->lanes[i];
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
         if (l.done) cudaEventDestroy(l.done);
@@ -257,7 +258,8 @@ int b200rx_destroy(b200rx_handle *h)
     for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->pipe_ev) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    for (int i = 0; i < 3; i++)
+        if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -275,7 +277,7 @@ int b200rx_synchronize(b200rx_handle *h)
 {
     if (!h) return B200RX_E_ARG;
     CU(h, cudaSetDevice(h->device));
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < B200RX_MAX_PIPELINE_DEPTH; i++)
         if (h->lanes[i].stream && h->lanes[i].used) CU(h, cudaStreamSynchronize(h->lanes[i].stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return B200RX_OK;
@@ -283,7 +285,7 @@ int b200rx_synchronize(b200rx_handle *h)
 
 int b200rx_set_pipeline_depth(b200rx_handle *h, uint32_t depth)
 {
-    if (!h || depth < 1 || depth > 3) return fail(h, B200RX_E_ARG, "b200rx_set_pipeline_depth: depth must be 1, 2 or 3");
+    if (!h || depth < 1 || depth > B200RX_MAX_PIPELINE_DEPTH) return fail(h, B200RX_E_ARG, "b200rx_set_pipeline_depth: depth must be 1 .. B200RX_MAX_PIPELINE_DEPTH");
     int rc = b200rx_synchronize(h);
     if (rc != B200RX_OK) return rc;
     const size_t nf = h->limits.max_frames;
@@ -485,10 +487,21 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
     const OutPtrs o{payload_out ? h->d_payload : nullptr, payload_stride, h->d_len, h->d_rate, h->d_status};
 
     // Chunked pipeline: the samples of chunk i+1 cross PCIe while chunk i is decoded (kernels of consecutive
-    // chunks alternate between two streams so that their Viterbi kernels overlap) and chunk i-1's results go
+    // chunks rotate over four streams so that their Viterbi kernels overlap) and chunk i-1's results go
     // back.  Needs the frames in stream order (lts1_index non-decreasing); otherwise one copy, one batch.
-    const uint32_t CH = 512;
-    bool ordered = n_frames > CH;
+    // The copy is the bottleneck, so what matters is how long the decode of the LAST chunk takes after its
+    // samples have landed: chunks start at CH frames and halve towards the end of the batch (down to CH_MIN).
+    static const uint32_t CH = [] { // tuning knobs for experiments
+        const char *e = getenv("B200RX_H2D_CHUNK");
+        long v = e ? atol(e) : 0;
+        return (uint32_t)(v >= 32 ? v : 1024);
+    }();
+    static const uint32_t CH_MIN = [] {
+        const char *e = getenv("B200RX_H2D_CHUNK_MIN");
+        long v = e ? atol(e) : 0;
+        return (uint32_t)(v >= 16 ? v : 64);
+    }();
+    bool ordered = n_frames > 2 * CH_MIN;
     for (uint32_t f = 1; ordered && f < n_frames; f++) ordered = lts1_index[f] >= lts1_index[f - 1];
     if (!ordered) {
         CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
@@ -501,7 +514,15 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
         CU(h, cudaStreamSynchronize(s));
         return B200RX_OK;
     }
-    const uint32_t n_chunks = (n_frames + CH - 1) / CH;
+    std::vector<uint32_t> bound(1, 0u); // chunk c = frames [bound[c], bound[c+1])
+    for (uint32_t f = 0; f < n_frames;) {
+        const uint32_t rest = n_frames - f;
+        uint32_t take = CH;
+        if (rest <= CH) take = rest <= CH_MIN ? rest : (rest / 2 > CH_MIN ? rest / 2 : CH_MIN);
+        f += take;
+        bound.push_back(f);
+    }
+    const uint32_t n_chunks = (uint32_t)bound.size() - 1;
     while (h->pipe_ev.size() < 2 * (size_t)n_chunks + 1) {
         cudaEvent_t e;
         CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -510,10 +531,10 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
     cudaEvent_t ev_start = h->pipe_ev[2 * n_chunks];
     CU(h, cudaEventRecord(ev_start, s)); // staging buffers (re)allocated, small arrays and counter reset queued
     CU(h, cudaStreamWaitEvent(h->copy_stream, ev_start, 0));
-    CU(h, cudaStreamWaitEvent(h->aux_stream, ev_start, 0));
+    for (int i = 0; i < 3; i++) CU(h, cudaStreamWaitEvent(h->aux_stream[i], ev_start, 0));
     uint64_t copied = 0; // samples [0, copied) are on their way
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t f0 = c * CH, f1 = (f0 + CH < n_frames) ? f0 + CH : n_frames;
+        const uint32_t f0 = bound[c], f1 = bound[c + 1];
         uint64_t hi = 0;
         for (uint32_t f = f0; f < f1; f++) {
             uint64_t e = lts1_index[f] + avail[f];
@@ -529,7 +550,7 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
         }
         cudaEvent_t ev_in = h->pipe_ev[2 * c], ev_out = h->pipe_ev[2 * c + 1];
         CU(h, cudaEventRecord(ev_in, h->copy_stream));
-        cudaStream_t cs = (c & 1) ? h->aux_stream : s;
+        cudaStream_t cs = (c & 3) ? h->aux_stream[(c & 3) - 1] : s;
         CU(h, cudaStreamWaitEvent(cs, ev_in, 0));
         int rc = launch_range(h, cs, f0, f1 - f0, h->d_iq, iq_samples, h->d_lts1, h->d_avail, o, nullptr, nullptr);
         if (rc != B200RX_OK) return rc;
@@ -544,7 +565,7 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
         CU(h, cudaMemcpyAsync(status + f0, h->d_status + f0, nf, cudaMemcpyDeviceToHost, h->d2h_stream));
     }
     CU(h, cudaStreamSynchronize(h->d2h_stream));
-    CU(h, cudaStreamSynchronize(h->aux_stream));
+    for (int i = 0; i < 3; i++) CU(h, cudaStreamSynchronize(h->aux_stream[i]));
     CU(h, cudaStreamSynchronize(s));
     return B200RX_OK;
 }

@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(64) viterbi_acs2_kernel(const FrameDesc *desc,
             }
             if (store) {
                 uint32_t *dst = d_blk + o * ACS2_WORDS_PER_8;
+#pragma unroll
+                for (int j = 0; j < NR / 2; j++) acc[j] ^= L.flip[o];
                 if constexpr (NR / 2 == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
                 else if constexpr (NR / 2 == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(acc[0], acc[1]);
                 else dst[0] = acc[0];

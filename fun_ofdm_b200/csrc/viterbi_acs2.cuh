@@ -18,7 +18,8 @@
 // cap = the other candidate the add + compare-select in one instruction).  The decision bit is
 // bit 8 / 24 of (survivor + 0x0100 - candidate_via_j+32) (set iff equal, i.e. iff j+32 won or tied) and is
 // computed with IMADs on the otherwise idle FMA pipe.  Decisions are accumulated over 8 steps per position
-// (acc = 2*acc + bits, one IMAD per 4 states) and stored as 64 B per frame per 8 steps.
+// (acc = 2*acc + bits, one IMAD per 4 states) and stored as 64 B per frame per 8 steps; in lane phases the
+// lanes holding predecessor j+32 accumulate the complement and flip it back with one XOR before the store.
 //
 // LB trades instructions for parallelism (ncu, 4096 frames x 12 096 steps): LB = 3 needs 11.0
 // warp-instructions per trellis step but gives 1024 warps for 592 schedulers (1 or 2 per scheduler, the
@@ -37,17 +38,15 @@ namespace b200rx {
 constexpr int ACS2_BLK = 24;          // steps per unrolled block = lcm(6 phases, 8-step store period)
 constexpr int ACS2_WORDS_PER_8 = 16;  // survivor words per frame per 8 steps
 
-__host__ __device__ __forceinline__ uint32_t acs2_rotl6(uint32_t x, int r)
+__host__ __device__ constexpr uint32_t acs2_rotl6(uint32_t x, int r)
 {
-    r %= 6;
-    return ((x << r) | (x >> (6 - r))) & 63u;
+    return ((x << (r % 6)) | (x >> (6 - r % 6))) & 63u;
 }
 
-__host__ __device__ __forceinline__ uint32_t acs2_class(uint32_t j)
+// Branch class of butterfly j: (parity(2j & 121), parity(2j & 91)).  GF(2)-linear in the bits of j.
+__host__ __device__ constexpr uint32_t acs2_class(uint32_t j)
 {
-    const uint32_t b0 = ((j >> 2) ^ (j >> 3) ^ (j >> 4)) & 1u; // parity(2j & 121)
-    const uint32_t b1 = (j ^ (j >> 2) ^ (j >> 3)) & 1u;        // parity(2j & 91)
-    return (b0 << 1) | b1;
+    return ((((j >> 2) ^ (j >> 3) ^ (j >> 4)) & 1u) << 1) | ((j ^ (j >> 2) ^ (j >> 3)) & 1u);
 }
 
 // PTX prmt in its default mode: selector nibble bit 3 replicates the sign bit of the selected byte, which
@@ -78,10 +77,21 @@ struct Acs2 {
     static constexpr int FPW = 32 / T;      // frames per warp
     static_assert(LB >= 2 && LB <= 4, "2, 3 or 4 lane bits");
 
+    // The class is linear in the position bits, so register i of a lane sees the lane's base class pair XOR
+    // xreg(phase, i) on both halves: registers with the same xreg share one metric pair (one PRMT).
+    static __host__ __device__ constexpr uint32_t xreg(int r, int i) { return acs2_class(acs2_rotl6((uint32_t)i << 1, r) & 31u); }
+    static __host__ __device__ constexpr bool xused(int r, uint32_t x)
+    {
+        for (int i = 0; i < NR; i++)
+            if (xreg(r, i) == x) return true;
+        return false;
+    }
+
     struct Lane {
-        uint32_t sel[6][NR]; // PRMT selector (hi class, lo class) per phase and register
-        uint32_t selB[NR];   // second selector of the half-bit phase
-        int sgn[LB], nsgn[LB];
+        uint32_t sel[6][4];  // PRMT selector (hi class, lo class) per phase and class offset x
+        uint32_t ck[LB];     // lane phases: 0x01000100 - (this lane holds predecessor j+32 ? 0x00010001 : 0)
+        uint32_t flip[3];    // decision bits this lane records inverted, per 8-step store of a 24-step block
+        uint32_t thr;        // renormalisation threshold on register 0 (lane 0 of the frame only)
         uint32_t neg1, one;  // 0xFFFFFFFF and 1 derived from a kernel argument so that ptxas keeps the IMADs
     };
 
@@ -89,27 +99,36 @@ struct Acs2 {
     {
         L.neg1 = neg1;
         L.one = 0u - neg1;
+        L.thr = glane == 0 ? 0x00D2FFFFu : 0xFFFFFFFFu;
+        const uint32_t p_hi = (uint32_t)glane << (6 - LB);
 #pragma unroll
         for (int r = 0; r < 6; r++) {
+            const uint32_t c_hi = acs2_class(acs2_rotl6(p_hi, r) & 31u);
+            const uint32_t c_lo = acs2_class(acs2_rotl6(p_hi | 1u, r) & 31u);
 #pragma unroll
-            for (int i = 0; i < NR; i++) {
-                const uint32_t p_hi = ((uint32_t)glane << (6 - LB)) | ((uint32_t)i << 1);
-                const uint32_t c_hi = acs2_class(acs2_rotl6(p_hi, r) & 31u);
-                const uint32_t c_lo = acs2_class(acs2_rotl6(p_hi | 1u, r) & 31u);
-                if (r < 5) L.sel[r][i] = 0x8080u | (c_hi << 8) | c_lo;
-                else {
-                    L.sel[r][i] = 0x8080u | (c_hi << 8) | (4u + c_hi);   // (m high, 63-m low)
-                    L.selB[i] = 0x8080u | ((4u + c_hi) << 8) | c_hi;     // (63-m high, m low)
-                }
+            for (uint32_t x = 0; x < 4; x++) {
+                if (r < 5) L.sel[r][x] = 0x8080u | ((c_hi ^ x) << 8) | (c_lo ^ x);
+                else L.sel[r][x] = 0x8080u | ((c_hi ^ x) << 8) | (4u + (c_hi ^ x)); // (m high, 63-m low)
             }
         }
+        // phase k < LB pairs lanes differing in lane bit (LB-1-k).  The lane holding predecessor j records
+        // "partner <= own" directly; the lane holding j+32 needs "own <= partner" and records its complement
+        // (own > partner, from the constant below), which is flipped back once per 8 steps before the store.
+        uint32_t inv[LB];
 #pragma unroll
         for (int k = 0; k < LB; k++) {
-            // phase r = k uses lane bit (LB-1-k); the lane holding predecessor j (bit 0) decides with
-            // "partner <= own", the lane holding j+32 with "own <= partner"
-            const int bit = (glane >> (LB - 1 - k)) & 1;
-            L.sgn[k] = bit ? -1 : 1;
-            L.nsgn[k] = bit ? 1 : -1;
+            inv[k] = (glane >> (LB - 1 - k)) & 1u;
+            L.ck[k] = ACS2_C - inv[k] * 0x00010001u;
+        }
+#pragma unroll
+        for (int o = 0; o < 3; o++) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int ph = (8 * o + i) % 6;
+                if (ph < LB) m |= inv[ph < LB ? ph : 0] << (7 - i);
+            }
+            L.flip[o] = m * 0x01010101u;
         }
     }
 
@@ -126,50 +145,67 @@ struct Acs2 {
     static __device__ __forceinline__ void step(uint32_t (&R)[NR], uint32_t (&D)[NR], uint32_t w, const Lane &L)
     {
         constexpr int axis = 5 - PH; // position bit separating the butterfly partners
-        if constexpr (axis >= 6 - LB) {
-            // ---- partners in another lane ----
-            constexpr int lbit = axis - (6 - LB);
-            constexpr int k = LB - 1 - lbit; // index into sgn[]
-            static_assert(k == PH, "lane phases come first");
+        if constexpr (axis >= 1) {
+            // metric pairs (m per half) and their complements (63 - m, psubusb 63, m), one per class offset in use
+            uint32_t Mv[4], Miv[4];
 #pragma unroll
-            for (int i = 0; i < NR; i++) {
-                const uint32_t M = acs2_prmt(w, w, L.sel[PH][i]);
-                const uint32_t Mi = acs2_fma(M, L.neg1, 0x003F003Fu);        // 63 - m per half (psubusb 63, m)
-                const uint32_t G = __viaddmin_u16x2(R[i], Mi, ACS2_CAP);       // my candidate for the partner's new state
-                const uint32_t S = __shfl_xor_sync(0xFFFFFFFFu, G, 1 << lbit); // partner's candidate for mine
-                const uint32_t V = __viaddmin_u16x2(R[i], M, ACS2_CAP);        // my own candidate
-                R[i] = __vminu2(V, S);
-                D[i] = (uint32_t)((int)V * L.sgn[k] + ((int)S * L.nsgn[k] + (int)ACS2_C));
+            for (uint32_t x = 0; x < 4; x++) {
+                Mv[x] = Miv[x] = 0;
+                if (xused(PH, x)) {
+                    Mv[x] = acs2_prmt(w, w, L.sel[PH][x]);
+                    Miv[x] = acs2_fma(Mv[x], L.neg1, 0x003F003Fu);
+                }
             }
-        } else if constexpr (axis >= 1) {
-            // ---- partners in another register of this lane ----
-            constexpr int q = axis - 1;
+            if constexpr (axis >= 6 - LB) {
+                // ---- partners in another lane ----
+                constexpr int lbit = axis - (6 - LB);
+                constexpr int k = LB - 1 - lbit; // index into ck[]
+                static_assert(k == PH, "lane phases come first");
 #pragma unroll
-            for (int a = 0; a < NR; a++) {
-                if ((a >> q) & 1) continue;
-                const int b = a | (1 << q);
-                const uint32_t M = acs2_prmt(w, w, L.sel[PH][a]);
-                const uint32_t Mi = acs2_fma(M, L.neg1, 0x003F003Fu);
-                const uint32_t B = __viaddmin_u16x2(R[b], Mi, ACS2_CAP); // via j+32 -> new state 2j
-                const uint32_t E = __viaddmin_u16x2(R[b], M, ACS2_CAP);  // via j+32 -> new state 2j+1
-                const uint32_t Ya = __viaddmin_u16x2(R[a], M, B);        // min(X[j] + m, B); ties keep B's value
-                const uint32_t Yb = __viaddmin_u16x2(R[a], Mi, E);
-                D[a] = acs2_fma(Ya, L.one, acs2_fma(B, L.neg1, ACS2_C));
-                D[b] = acs2_fma(Yb, L.one, acs2_fma(E, L.neg1, ACS2_C));
-                R[a] = Ya;
-                R[b] = Yb;
+                for (int i = 0; i < NR; i++) {
+                    const uint32_t M = Mv[xreg(PH, i)], Mi = Miv[xreg(PH, i)];
+                    const uint32_t G = __viaddmin_u16x2(R[i], Mi, ACS2_CAP);       // my candidate for the partner's new state
+                    const uint32_t S = __shfl_xor_sync(0xFFFFFFFFu, G, 1 << lbit); // partner's candidate for mine
+                    const uint32_t V = __viaddmin_u16x2(R[i], M, ACS2_CAP);        // my own candidate
+                    R[i] = __vminu2(V, S);
+                    D[i] = acs2_fma(V, L.one, acs2_fma(S, L.neg1, L.ck[k]));       // bit 8/24: own >= partner (or >, see ck)
+                }
+            } else {
+                // ---- partners in another register of this lane ----
+                constexpr int q = axis - 1;
+#pragma unroll
+                for (int a = 0; a < NR; a++) {
+                    if ((a >> q) & 1) continue;
+                    const int b = a | (1 << q);
+                    const uint32_t M = Mv[xreg(PH, a)], Mi = Miv[xreg(PH, a)];
+                    const uint32_t B = __viaddmin_u16x2(R[b], Mi, ACS2_CAP); // via j+32 -> new state 2j
+                    const uint32_t E = __viaddmin_u16x2(R[b], M, ACS2_CAP);  // via j+32 -> new state 2j+1
+                    const uint32_t Ya = __viaddmin_u16x2(R[a], M, B);        // min(X[j] + m, B); ties keep B's value
+                    const uint32_t Yb = __viaddmin_u16x2(R[a], Mi, E);
+                    D[a] = acs2_fma(Ya, L.one, acs2_fma(B, L.neg1, ACS2_C));
+                    D[b] = acs2_fma(Yb, L.one, acs2_fma(E, L.neg1, ACS2_C));
+                    R[a] = Ya;
+                    R[b] = Yb;
+                }
             }
         } else {
             // ---- partners are the two halves of one register: high = state j, low = state j+32 ----
             const uint32_t wc = w ^ 0x3F3F3F3Fu; // 63 - m per byte
+            uint32_t MAv[4], MBv[4];
+#pragma unroll
+            for (uint32_t x = 0; x < 4; x++) {
+                MAv[x] = MBv[x] = 0;
+                if (xused(PH, x)) {
+                    MAv[x] = acs2_prmt(w, wc, L.sel[PH][x]);              // (m, 63-m)
+                    MBv[x] = acs2_fma(MAv[x], L.neg1, 0x003F003Fu);       // (63-m, m)
+                }
+            }
 #pragma unroll
             for (int i = 0; i < NR; i++) {
                 const uint32_t W = __byte_perm(R[i], R[i], 0x3232u); // (X[j], X[j])
                 const uint32_t Z = __byte_perm(R[i], R[i], 0x1010u); // (X[j+32], X[j+32])
-                const uint32_t MA = acs2_prmt(w, wc, L.sel[PH][i]);  // (m, 63-m)
-                const uint32_t MB = acs2_prmt(w, wc, L.selB[i]);     // (63-m, m)
-                const uint32_t V = __viaddmin_u16x2(Z, MB, ACS2_CAP); // via j+32: (-> 2j, -> 2j+1)
-                const uint32_t Y = __viaddmin_u16x2(W, MA, V);
+                const uint32_t V = __viaddmin_u16x2(Z, MBv[xreg(PH, i)], ACS2_CAP); // via j+32: (-> 2j, -> 2j+1)
+                const uint32_t Y = __viaddmin_u16x2(W, MAv[xreg(PH, i)], V);
                 D[i] = acs2_fma(Y, L.one, acs2_fma(V, L.neg1, ACS2_C));
                 R[i] = Y;
             }
@@ -178,9 +214,9 @@ struct Acs2 {
 
     // Reference renormalisation (viterbi.cpp:314-332): if metric of state 0 > 210, subtract the minimum of
     // all 64 metrics.  State 0 always sits in the high half of register 0 of the frame's lane 0.
-    static __device__ __forceinline__ void renorm(uint32_t (&R)[NR], int glane, int group)
+    static __device__ __forceinline__ void renorm(uint32_t (&R)[NR], const Lane &L, int group)
     {
-        const bool hot = (glane == 0) && (R[0] > 0x00D2FFFFu);
+        const bool hot = R[0] > L.thr;
         if (__any_sync(0xFFFFFFFFu, hot)) {
             const uint32_t any = __ballot_sync(0xFFFFFFFFu, hot);
             uint32_t m = R[0];
@@ -205,7 +241,7 @@ struct Acs2 {
         // bytes 1 and 3 of each raw decision word are 0/1: gather 4 of them, shift into the 8-step history
 #pragma unroll
         for (int j = 0; j < NR / 2; j++) acc[j] = acc[j] * 2u + __byte_perm(D[2 * j], D[2 * j + 1], 0x7531u);
-        renorm(R, glane, group);
+        renorm(R, L, group);
     }
 };
 

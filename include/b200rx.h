@@ -105,8 +105,10 @@ B200RX_API const char *b200rx_version(void);
 B200RX_API int b200rx_set_stream(b200rx_handle *h, void *cuda_stream);
 B200RX_API int b200rx_synchronize(b200rx_handle *h);
 
+#define B200RX_MAX_PIPELINE_DEPTH 6
+
 /* Pipelining of consecutive b200rx_decode_batch_dev calls.  depth = 1 (default): every call runs in order on
- * the handle's stream.  depth = 2 or 3: calls rotate over `depth` lanes, each with its own scratch set and
+ * the handle's stream.  depth = 2 .. B200RX_MAX_PIPELINE_DEPTH: calls rotate over `depth` lanes, each with its own scratch set and
  * stream, so that batch j+1 is already in its front end while batch j is still in its Viterbi kernel (the
  * Viterbi kernel of one 4096-frame batch cannot fill a B200: +32 % / +43 % throughput measured at depth 2 / 3).
  * A call still only reads its inputs after everything queued before it on the handle's stream, but its
