@@ -58,6 +58,19 @@ struct b200rx_handle {
     cudaStream_t copy_stream = nullptr, aux_stream[3] = {nullptr, nullptr, nullptr}, d2h_stream = nullptr;
     std::vector<cudaEvent_t> pipe_ev; // 2 per chunk: samples landed, results ready
 
+    // frame detection / timing synchronisation scratch (allocated by the first sync / receive call)
+    uint64_t *sy_ev_x = nullptr;
+    uint32_t *sy_ev_count = nullptr;
+    uint32_t sy_ev_cap = 0;
+    SyncRec *sy_rec = nullptr;
+    uint32_t *sy_order = nullptr;
+    uint64_t *sy_lts1 = nullptr;
+    uint32_t *sy_avail = nullptr;
+    FrameRot *sy_rot = nullptr;
+    double *sy_phase = nullptr;
+    SyncSummary *sy_summary = nullptr;      // device
+    SyncSummary *sy_summary_host = nullptr; // pinned
+
     uint64_t launches = 0;
     std::string error;
 };
@@ -132,6 +145,8 @@ cudaError_t b200rx::upload_tables()
         pol[i] = fb ? -1 : 1;
     }
     cudaError_t e = upload_frontend_tables(tw, pol);
+    if (e != cudaSuccess) return e;
+    e = upload_sync_tables();
     if (e != cudaSuccess) return e;
 
     // CRC-32/ISO-HDLC slice-by-4 tables
@@ -250,6 +265,9 @@ int b200rx_destroy(b200rx_handle *h)
         if (i > 0) { cudaFree(l.desc); cudaFree(l.bm); cudaFree(l.dec); cudaFree(l.counters); }
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
+    cudaFree(h->sy_ev_x); cudaFree(h->sy_ev_count); cudaFree(h->sy_rec); cudaFree(h->sy_order); cudaFree(h->sy_lts1);
+    cudaFree(h->sy_avail); cudaFree(h->sy_rot); cudaFree(h->sy_phase); cudaFree(h->sy_summary);
+    if (h->sy_summary_host) cudaFreeHost(h->sy_summary_host);
     use_lane(h, 0);
     cudaFree(h->desc); cudaFree(h->bm); cudaFree(h->dec); cudaFree(h->counters);
     cudaFree(h->d_iq); cudaFree(h->d_lts1); cudaFree(h->d_avail); cudaFree(h->d_payload);
@@ -363,7 +381,7 @@ struct OutPtrs { uint8_t *payload; uint32_t stride; uint16_t *len; uint8_t *rate
 // K1 -> K2 -> K3 for frames [off, off + n) of the batch on stream s; ev (4 events) optional.
 int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, const double *iq_dev, uint64_t iq_samples,
                  const uint64_t *lts1_dev, const uint32_t *avail_dev, const OutPtrs &o, const b200rx_debug *dbg,
-                 cudaEvent_t *ev)
+                 cudaEvent_t *ev, const FrameRot *rot_dev = nullptr)
 {
     const size_t S = h->max_steps;
     FrontendArgs fa{};
@@ -377,6 +395,7 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
     fa.bm_stride = h->max_steps;
     fa.max_steps = h->max_steps;
     fa.max_len = h->limits.max_payload_bytes;
+    fa.rot = rot_dev ? rot_dev + off : nullptr;
     if (dbg) {
         fa.dbg_eq = dbg->equalized ? reinterpret_cast<double2 *>(dbg->equalized) + (size_t)off * dbg->eq_vectors * 48 : nullptr;
         fa.dbg_eq_vectors = dbg->eq_vectors;
@@ -566,6 +585,151 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
     }
     CU(h, cudaStreamSynchronize(h->d2h_stream));
     for (int i = 0; i < 3; i++) CU(h, cudaStreamSynchronize(h->aux_stream[i]));
+    CU(h, cudaStreamSynchronize(s));
+    return B200RX_OK;
+}
+
+namespace {
+
+int ensure_sync_scratch(b200rx_handle *h)
+{
+    if (h->sy_summary_host) return B200RX_OK;
+    const size_t nf = h->limits.max_frames;
+    h->sy_ev_cap = (uint32_t)(2 * nf + 64);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void **)&h->sy_ev_x, h->sy_ev_cap * sizeof(uint64_t));
+    A((void **)&h->sy_ev_count, sizeof(uint32_t));
+    A((void **)&h->sy_rec, h->sy_ev_cap * sizeof(SyncRec));
+    A((void **)&h->sy_order, h->sy_ev_cap * sizeof(uint32_t));
+    A((void **)&h->sy_lts1, nf * sizeof(uint64_t));
+    A((void **)&h->sy_avail, nf * sizeof(uint32_t));
+    A((void **)&h->sy_rot, nf * sizeof(FrameRot));
+    A((void **)&h->sy_phase, nf * sizeof(double));
+    A((void **)&h->sy_summary, sizeof(SyncSummary));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->sy_summary_host, sizeof(SyncSummary), cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "sync scratch", e);
+    return B200RX_OK;
+}
+
+// detector + timing sync on stream s into the handle's scratch; returns with the summary on the host
+int run_sync(b200rx_handle *h, cudaStream_t s, const double *iq_dev, uint64_t n_samples, double phase_in, uint8_t *tags_dev)
+{
+    int rc = ensure_sync_scratch(h);
+    if (rc != B200RX_OK) return rc;
+    SyncArgs a{};
+    a.iq = reinterpret_cast<const double2 *>(iq_dev);
+    a.n_samples = n_samples;
+    a.rot_in = make_double2(cos(phase_in), sin(phase_in)); // timing_sync.cpp:124
+    a.max_frames = h->limits.max_frames;
+    a.tags = tags_dev;
+    a.ev_x = h->sy_ev_x; a.ev_count = h->sy_ev_count; a.ev_cap = h->sy_ev_cap;
+    a.rec = h->sy_rec; a.order = h->sy_order;
+    a.lts1 = h->sy_lts1; a.avail = h->sy_avail; a.rot = h->sy_rot; a.phase = h->sy_phase;
+    a.summary = h->sy_summary;
+    CU(h, launch_sync(a, s));
+    h->launches += n_samples ? 3 : 1;
+    CU(h, cudaMemcpyAsync(h->sy_summary_host, h->sy_summary, sizeof(SyncSummary), cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    if (!h->sy_summary_host->phase_valid) h->sy_summary_host->last_phase = phase_in;
+    return B200RX_OK;
+}
+
+int drain_lanes(b200rx_handle *h)
+{
+    if (h->depth > 1) { // not pipelined: drain the lanes, work on scratch set 0
+        int rcq = b200rx_synchronize(h);
+        if (rcq != B200RX_OK) return rcq;
+        use_lane(h, 0);
+    }
+    return B200RX_OK;
+}
+
+} // namespace
+
+int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in, uint8_t *tags_dev,
+                    uint64_t *lts1_index_dev, uint32_t *avail_dev, double *phase_dev, b200rx_sync_result *res)
+{
+    if (!h) return B200RX_E_ARG;
+    if ((!iq_dev && n_samples) || !res) return fail(h, B200RX_E_ARG, "b200rx_sync_dev: null argument");
+    CU(h, cudaSetDevice(h->device));
+    int rc = drain_lanes(h);
+    if (rc != B200RX_OK) return rc;
+    cudaStream_t s = h->stream;
+    rc = run_sync(h, s, iq_dev, n_samples, phase_in, tags_dev);
+    if (rc != B200RX_OK) return rc;
+    *res = *h->sy_summary_host;
+    const size_t nf = res->n_frames;
+    if (nf) {
+        if (lts1_index_dev) CU(h, cudaMemcpyAsync(lts1_index_dev, h->sy_lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        if (avail_dev) CU(h, cudaMemcpyAsync(avail_dev, h->sy_avail, nf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        if (phase_dev) CU(h, cudaMemcpyAsync(phase_dev, h->sy_phase, nf * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CU(h, cudaStreamSynchronize(s));
+    }
+    return B200RX_OK;
+}
+
+int b200rx_receive_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
+                       uint8_t *payload_out_dev, uint32_t payload_stride, uint16_t *payload_len_dev, uint8_t *rate_out_dev,
+                       uint8_t *status_dev, uint64_t *lts1_out_dev, b200rx_sync_result *res)
+{
+    if (!h) return B200RX_E_ARG;
+    if ((!iq_dev && n_samples) || !status_dev || !res) return fail(h, B200RX_E_ARG, "b200rx_receive_dev: null argument");
+    CU(h, cudaSetDevice(h->device));
+    int rc = drain_lanes(h);
+    if (rc != B200RX_OK) return rc;
+    cudaStream_t s = h->stream;
+    cudaEvent_t *ev = call_events(h);
+    CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
+    rc = run_sync(h, s, iq_dev, n_samples, phase_in, nullptr);
+    if (rc != B200RX_OK) return rc;
+    *res = *h->sy_summary_host;
+    const uint32_t nf = res->n_frames;
+    if (nf == 0) return B200RX_OK;
+    if (lts1_out_dev) CU(h, cudaMemcpyAsync(lts1_out_dev, h->sy_lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    const OutPtrs o{payload_out_dev, payload_stride, payload_len_dev, rate_out_dev, status_dev};
+    rc = launch_range(h, s, 0, nf, iq_dev, n_samples, h->sy_lts1, h->sy_avail, o, nullptr, ev, h->sy_rot);
+    if (rc != B200RX_OK) return rc;
+    if (ev == h->ev) h->ev_valid = true;
+    return B200RX_OK;
+}
+
+int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, double phase_in, uint8_t *payload_out,
+                   uint32_t payload_stride, uint16_t *payload_len, uint8_t *rate_out, uint8_t *status, uint64_t *lts1_out,
+                   b200rx_sync_result *res)
+{
+    if (!h) return B200RX_E_ARG;
+    if ((!iq && n_samples) || !status || !res) return fail(h, B200RX_E_ARG, "b200rx_receive: null argument");
+    CU(h, cudaSetDevice(h->device));
+    int rc = drain_lanes(h);
+    if (rc != B200RX_OK) return rc;
+    cudaStream_t s = h->stream;
+    const size_t iq_bytes = (size_t)n_samples * 2 * sizeof(double);
+    if (iq_bytes > h->d_iq_cap) {
+        if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_receive: sample staging", e);
+        h->d_iq_cap = iq_bytes;
+    }
+    const size_t pl_cap = payload_out ? (size_t)h->limits.max_frames * payload_stride : 0;
+    if (pl_cap > h->d_payload_cap) {
+        if (h->d_payload) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_payload); h->d_payload = nullptr; h->d_payload_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->d_payload, pl_cap);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_receive: payload staging", e);
+        h->d_payload_cap = pl_cap;
+    }
+    if (iq_bytes) CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    rc = b200rx_receive_dev(h, h->d_iq, n_samples, phase_in, payload_out ? h->d_payload : nullptr, payload_stride, h->d_len,
+                            h->d_rate, h->d_status, nullptr, res);
+    if (rc != B200RX_OK) return rc;
+    const size_t nf = res->n_frames;
+    if (nf) {
+        if (payload_out) CU(h, cudaMemcpyAsync(payload_out, h->d_payload, nf * payload_stride, cudaMemcpyDeviceToHost, s));
+        if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+        if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, nf, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(status, h->d_status, nf, cudaMemcpyDeviceToHost, s));
+        if (lts1_out) CU(h, cudaMemcpyAsync(lts1_out, h->sy_lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    }
     CU(h, cudaStreamSynchronize(s));
     return B200RX_OK;
 }

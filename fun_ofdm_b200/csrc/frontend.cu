@@ -162,6 +162,25 @@ __device__ __forceinline__ void step_symbols(const uint8_t *soft, int punc, int 
     }
 }
 
+// Sample fetch.  ROT: multiply by the constant rotation timing_sync applies (timing_sync.cpp:121-125:
+// input[x].sample *= (cos(m_phase_acc), sin(m_phase_acc)); std::complex operator*= evaluated without contraction).
+struct RotCtx {
+    double2 rn, ro;  // rotation for relative index >= from / < from
+    int64_t from;    // relative to the frame's LTS1
+};
+
+template <bool ROT>
+__device__ __forceinline__ double2 fetch(const double2 *win, int k, const RotCtx &rc)
+{
+    double2 v = win[k];
+    if constexpr (ROT) {
+        const double2 r = ((int64_t)k >= rc.from) ? rc.rn : rc.ro;
+        v = make_double2(__dsub_rn(__dmul_rn(v.x, r.x), __dmul_rn(v.y, r.y)),
+                         __dadd_rn(__dmul_rn(v.x, r.y), __dmul_rn(v.y, r.x)));
+    }
+    return v;
+}
+
 struct SymbolCtx {
     const double2 *tw;   // smem twiddles
     const double2 *hinv; // smem inverse channel
@@ -171,10 +190,11 @@ struct SymbolCtx {
 
 // One OFDM symbol: samples -> equalised, derotated data carriers -> soft bits in ctx.soft.
 // v = symbol index from SIGNAL (0) on: selects the pilot polarity (phase_tracker.cpp:77-86).
-__device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const double2 *win, int v, int bpsc, int lane,
-                                               double2 *dbg_eq)
+template <bool ROT>
+__device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const double2 *win, int off, const RotCtx &rc, int v,
+                                               int bpsc, int lane, double2 *dbg_eq)
 {
-    double2 v0 = win[lane], v1 = win[lane + 32];
+    double2 v0 = fetch<ROT>(win, off + lane, rc), v1 = fetch<ROT>(win, off + lane + 32, rc);
     warp_fft64(v0, v1, ctx.tw, lane);
     ctx.xs[shifted_index(lane, 0)] = v0;
     ctx.xs[shifted_index(lane, 1)] = v1;
@@ -216,6 +236,7 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const doubl
     __syncwarp();
 }
 
+template <bool ROT>
 __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 {
     __shared__ double2 s_tw[64];
@@ -233,6 +254,13 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     if (p >= a.iq_samples) avail = 0;
     else if ((uint64_t)avail > a.iq_samples - p) avail = (uint32_t)(a.iq_samples - p);
     const double2 *win = a.iq + p;
+    RotCtx rc{};
+    if constexpr (ROT) {
+        const FrameRot fr = a.rot[frame];
+        rc.rn = fr.rot_new;
+        rc.ro = fr.rot_old;
+        rc.from = (int64_t)fr.from - (int64_t)p;
+    }
 
     if (tid < 64) s_tw[tid] = c_twiddle[tid];
     if (tid < FE_WARPS) s_soft[tid][ERASURE_AT] = 127;
@@ -253,7 +281,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 
     // ---- channel estimate: channel_est.cpp:53-58, H^-1[j] = sum_{2 LTS} L[j] / R[j] / 2 for all 64 bins ----
     if (warp < 2) {
-        double2 v0 = win[64 * warp + lane], v1 = win[64 * warp + lane + 32];
+        double2 v0 = fetch<ROT>(win, 64 * warp + lane, rc), v1 = fetch<ROT>(win, 64 * warp + lane + 32, rc);
         warp_fft64(v0, v1, s_tw, lane);
 #pragma unroll
         for (int slot = 0; slot < 2; slot++) {
@@ -272,7 +300,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     // ---- SIGNAL: ppdu.cpp:168-218 ----
     if (warp == 0) {
         double2 *dbg = a.dbg_eq ? a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors) * 48 : nullptr;
-        process_symbol(ctx, win + 128 + 16, 0, 1, lane, (dbg && a.dbg_eq_vectors > 0) ? dbg : nullptr);
+        process_symbol<ROT>(ctx, win, 128 + 16, rc, 0, 1, lane, (dbg && a.dbg_eq_vectors > 0) ? dbg : nullptr);
         if (lane < 24) {
             uint32_t s0, s1;
             step_symbols(ctx.soft, PUNC_1_2, lane, s0, s1);
@@ -319,7 +347,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     for (uint32_t s = warp; s < nsym; s += FE_WARPS) {
         double2 *dbg = nullptr;
         if (a.dbg_eq && s + 1 < a.dbg_eq_vectors) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors + s + 1) * 48;
-        process_symbol(ctx, win + 128 + 80 * (size_t)(s + 1) + 16, (int)(s + 1), rr.bpsc, lane, dbg);
+        process_symbol<ROT>(ctx, win, 128 + 80 * (int)(s + 1) + 16, rc, (int)(s + 1), rr.bpsc, lane, dbg);
         uint32_t *sym_out = bm_out + (size_t)s * rr.dbps;
         for (int t = lane; t < rr.dbps; t += 32) {
             const uint32_t pair = s_idx[t];
@@ -354,7 +382,8 @@ cudaError_t upload_frontend_tables(const double2 *tw, const int8_t *pol)
 cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s)
 {
     if (a.n_frames == 0) return cudaSuccess;
-    frontend_kernel<<<a.n_frames, FE_WARPS * 32, 0, s>>>(a);
+    if (a.rot) frontend_kernel<true><<<a.n_frames, FE_WARPS * 32, 0, s>>>(a);
+    else frontend_kernel<false><<<a.n_frames, FE_WARPS * 32, 0, s>>>(a);
     return cudaGetLastError();
 }
 

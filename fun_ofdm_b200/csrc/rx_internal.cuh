@@ -95,6 +95,44 @@ __host__ __device__ __forceinline__ uint32_t branch_class(uint32_t j)
     return (b0 << 1) | b1;
 }
 
+// ---- frame detection / timing synchronisation (sync.cu) ----
+struct SyncRec {      // outcome of one STS_END event (timing_sync.cpp:71-118)
+    uint64_t x;       // stream index of the STS_END tag
+    int64_t lts1;     // stream index tagged LTS1 (valid when found)
+    double2 rot;      // (cos, sin) of the phase set by this event
+    double phase;
+    uint32_t found, n_peaks;
+};
+
+struct FrameRot {     // constant rotation timing_sync applies to the samples of a frame (timing_sync.cpp:121-125)
+    double2 rot_new;  // samples at stream index >= from
+    double2 rot_old;  // samples before (the phase the previous frame left behind)
+    uint64_t from;    // stream index of the frame's STS_END tag
+};
+
+typedef b200rx_sync_result SyncSummary;
+
+struct SyncArgs {
+    const double2 *iq;
+    uint64_t n_samples;
+    double2 rot_in;       // (cos, sin) of m_phase_acc before the stream
+    uint32_t max_frames;
+    uint8_t *tags;        // [n_samples] or null
+    uint64_t *ev_x;       // scratch [ev_cap]
+    uint32_t *ev_count;   // scratch
+    uint32_t ev_cap;
+    SyncRec *rec;         // scratch [ev_cap]
+    uint32_t *order;      // scratch [ev_cap]
+    uint64_t *lts1;       // [max_frames]
+    uint32_t *avail;      // [max_frames]
+    FrameRot *rot;        // [max_frames]
+    double *phase;        // [max_frames] or null
+    SyncSummary *summary; // device
+};
+
+cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s);
+cudaError_t upload_sync_tables();
+
 // ---- launchers (each returns the cudaError_t of the launch) ----
 struct FrontendArgs {
     const double2 *iq;
@@ -108,6 +146,7 @@ struct FrontendArgs {
     uint32_t max_steps;
     uint32_t max_len;
     int header_only;         // 1: stop after the SIGNAL symbol (descriptor only, no branch metrics)
+    const FrameRot *rot;     // per frame, or null: samples are used as they are
     // taps (may be null)
     double2 *dbg_eq;
     uint32_t dbg_eq_vectors;

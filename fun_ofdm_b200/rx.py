@@ -48,6 +48,15 @@ class Stats(C.Structure):
                 ("traceback_rewalks", C.c_uint64)]
 
 
+class SyncResult(C.Structure):
+    _fields_ = [("n_events", C.c_uint32), ("n_frames", C.c_uint32), ("overflow", C.c_uint32), ("reserved", C.c_uint32),
+                ("last_phase", C.c_double), ("phase_valid", C.c_uint32), ("pad", C.c_uint32)]
+
+    def as_dict(self):
+        return {"n_events": int(self.n_events), "n_frames": int(self.n_frames), "overflow": int(self.overflow),
+                "last_phase": float(self.last_phase), "phase_valid": bool(self.phase_valid)}
+
+
 def lib_path():
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libb200rx.so")
 
@@ -93,6 +102,12 @@ def load_library():
     L.b200rx_decode_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp]
     L.b200rx_decode_batch_dev.restype = C.c_int
     L.b200rx_decode_batch_dev.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp, C.POINTER(Debug)]
+    L.b200rx_sync_dev.restype = C.c_int
+    L.b200rx_sync_dev.argtypes = [vp, vp, u64, C.c_double, vp, vp, vp, vp, C.POINTER(SyncResult)]
+    L.b200rx_receive_dev.restype = C.c_int
+    L.b200rx_receive_dev.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, C.POINTER(SyncResult)]
+    L.b200rx_receive.restype = C.c_int
+    L.b200rx_receive.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, C.POINTER(SyncResult)]
     L.b200rx_viterbi_batch_dev.restype = C.c_int
     L.b200rx_viterbi_batch_dev.argtypes = [vp, vp, u64, vp, u32, u32, vp, u32]
     L.b200rx_get_stats.restype = C.c_int
@@ -250,6 +265,52 @@ class Receiver:
             _ptr(payload), int(payload.shape[1]) if payload is not None else 0,
             _ptr(length), _ptr(rate), _ptr(status), C.byref(dbg) if dbg is not None else None)
         self._check(rc, "b200rx_decode_batch_dev")
+
+    # ---- raw sample streams: frame_detector + timing_sync (+ decode) ----
+    def sync_dev(self, iq, phase_in=0.0, tags=None, lts1_index=None, avail=None, phase=None):
+        """iq: CUDA tensor float64 [2*n] / complex128 [n].  Optional outputs: tags uint8 [n], lts1_index int64
+        [max_frames], avail int32 [max_frames], phase float64 [max_frames].  Returns the summary dict."""
+        n = int(iq.numel() if iq.is_complex() else iq.numel() // 2)
+        res = SyncResult()
+        rc = self.lib.b200rx_sync_dev(self.h, _ptr(iq), n, float(phase_in), _ptr(tags), _ptr(lts1_index), _ptr(avail),
+                                      _ptr(phase), C.byref(res))
+        self._check(rc, "b200rx_sync_dev")
+        return res.as_dict()
+
+    def receive_dev(self, iq, payload, length, rate, status, lts1_index=None, phase_in=0.0):
+        """Raw samples (CUDA tensor) -> payloads of the frames found, in stream order.  Output tensors are sized for
+        max_frames; entries [0, n_frames) are valid after synchronize().  Returns the summary dict."""
+        n = int(iq.numel() if iq.is_complex() else iq.numel() // 2)
+        res = SyncResult()
+        rc = self.lib.b200rx_receive_dev(self.h, _ptr(iq), n, float(phase_in), _ptr(payload),
+                                         int(payload.shape[1]) if payload is not None else 0, _ptr(length), _ptr(rate),
+                                         _ptr(status), _ptr(lts1_index), C.byref(res))
+        self._check(rc, "b200rx_receive_dev")
+        return res.as_dict()
+
+    def receive(self, samples, phase_in=0.0):
+        """Host samples (complex128 array) -> (list of payload bytes of CRC-OK frames in stream order, info dict with
+        per-frame status / length / rate / lts1 and the sync summary).  Mirrors receiver_chain::process_samples
+        (receiver_chain.cpp:106-126) for one contiguous capture."""
+        iq = np.ascontiguousarray(samples, dtype=np.complex128)
+        n = int(iq.size)
+        mf, stride = self.max_frames, max(1, self.max_payload_bytes)
+        payload = np.zeros((mf, stride), dtype=np.uint8)
+        length = np.zeros(mf, dtype=np.uint16)
+        rate = np.zeros(mf, dtype=np.uint8)
+        status = np.zeros(mf, dtype=np.uint8)
+        lts1 = np.zeros(mf, dtype=np.uint64)
+        res = SyncResult()
+        rc = self.lib.b200rx_receive(self.h, iq.ctypes.data_as(C.c_void_p), n, float(phase_in),
+                                     payload.ctypes.data_as(C.c_void_p), stride, length.ctypes.data_as(C.c_void_p),
+                                     rate.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
+                                     lts1.ctypes.data_as(C.c_void_p), C.byref(res))
+        self._check(rc, "b200rx_receive")
+        nf = int(res.n_frames)
+        out = [bytes(payload[f, : length[f]]) for f in range(nf) if status[f] == ST_OK]
+        info = dict(res.as_dict(), status=status[:nf].copy(), length=length[:nf].copy(), rate=rate[:nf].copy(),
+                    lts1=lts1[:nf].copy())
+        return out, info
 
     def viterbi_batch_dev(self, symbols, data_bits, max_data_bits, out):
         """symbols uint8 [n, stride] depunctured soft symbols; data_bits int32 [n]; out uint8 [n, out_stride]."""

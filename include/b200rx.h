@@ -154,6 +154,43 @@ B200RX_API int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, u
                             uint16_t *payload_len_dev, uint8_t *rate_out_dev, uint8_t *status_dev,
                             const b200rx_debug *dbg);
 
+/* ---- frame detection + timing synchronisation + decode from a raw sample stream ----
+ * Replaces frame_detector::work (frame_detector.cpp:41-92) and timing_sync::work (timing_sync.cpp:51-139) in
+ * front of the four hot-path blocks, i.e. together with the decode it is receiver_chain::process_samples
+ * (receiver_chain.cpp:106-126) for one contiguous capture.  Tags are the reference's vector_tag values
+ * (tagged_vector.h:25-34: 1 STS_START, 2 STS_END, 4 LTS1, 5 LTS2), indexed by the sample they sit on (the
+ * reference's timing_sync output is the same stream delayed by 160 samples).  STS_END tags in the last 160
+ * samples are left for the next capture, as in the reference (timing_sync.cpp:68). */
+typedef struct b200rx_sync_result {
+    uint32_t n_events;    /* STS_END tags examined */
+    uint32_t n_frames;    /* LTS1 tags placed = frames handed to the decoder, in stream order */
+    uint32_t overflow;    /* events / frames dropped because the handle's max_frames was too small */
+    uint32_t reserved;
+    double last_phase;    /* m_phase_acc after the capture (timing_sync.h:45); feed it to the next call */
+    uint32_t phase_valid; /* 0: no frame was found, the phase is still phase_in */
+    uint32_t pad;
+} b200rx_sync_result;
+
+/* Tags and frame list only.  tags_dev [n_samples] (nullable); lts1_index_dev / avail_dev [max_frames] as consumed by
+ * b200rx_decode_batch_dev; phase_dev [max_frames] (nullable) the rotation phase of each frame.  phase_in is
+ * m_phase_acc before the capture (0 for a fresh chain).  Synchronous: returns when `res` (host) is filled. */
+B200RX_API int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
+                               uint8_t *tags_dev, uint64_t *lts1_index_dev, uint32_t *avail_dev, double *phase_dev,
+                               b200rx_sync_result *res);
+
+/* Raw samples in HBM -> payloads: detection, synchronisation, phase rotation and the hot path.  Outputs are
+ * device arrays sized for max_frames; entries [0, res->n_frames) are valid once the handle's stream has been
+ * synchronised.  lts1_out_dev (nullable) receives the LTS1 index of every frame. */
+B200RX_API int b200rx_receive_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
+                                  uint8_t *payload_out_dev, uint32_t payload_stride, uint16_t *payload_len_dev,
+                                  uint8_t *rate_out_dev, uint8_t *status_dev, uint64_t *lts1_out_dev,
+                                  b200rx_sync_result *res);
+
+/* Same with host buffers (pinned buffers recommended); synchronous. */
+B200RX_API int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, double phase_in,
+                              uint8_t *payload_out, uint32_t payload_stride, uint16_t *payload_len, uint8_t *rate_out,
+                              uint8_t *status, uint64_t *lts1_out, b200rx_sync_result *res);
+
 /* Replaces ppdu::decode_header (ppdu.cpp:168-218) for n_frames frames: only the two LTS symbols and the
  * SIGNAL symbol are read (208 samples from lts1_index[f]); gives the streaming adapter the frame length
  * before the frame has fully arrived.  HOST buffers, synchronous.  status: B200RX_ST_OK (header valid; the
