@@ -58,17 +58,20 @@ struct b200rx_handle {
     cudaStream_t copy_stream = nullptr, aux_stream[3] = {nullptr, nullptr, nullptr}, d2h_stream = nullptr;
     std::vector<cudaEvent_t> pipe_ev; // 2 per chunk: samples landed, results ready
 
-    // frame detection / timing synchronisation scratch (allocated by the first sync / receive call)
-    uint64_t *sy_ev_x = nullptr;
-    uint32_t *sy_ev_count = nullptr;
+    // frame detection / timing synchronisation scratch, one set per pipeline lane (allocated on first use)
+    struct SyncScratch {
+        uint64_t *ev_x = nullptr;
+        uint32_t *ev_count = nullptr;
+        SyncRec *rec = nullptr;
+        uint32_t *order = nullptr;
+        uint64_t *lts1 = nullptr;
+        uint32_t *avail = nullptr;
+        FrameRot *rot = nullptr;
+        double *phase = nullptr;
+        SyncSummary *summary = nullptr; // device
+    };
+    SyncScratch sy[B200RX_MAX_PIPELINE_DEPTH];
     uint32_t sy_ev_cap = 0;
-    SyncRec *sy_rec = nullptr;
-    uint32_t *sy_order = nullptr;
-    uint64_t *sy_lts1 = nullptr;
-    uint32_t *sy_avail = nullptr;
-    FrameRot *sy_rot = nullptr;
-    double *sy_phase = nullptr;
-    SyncSummary *sy_summary = nullptr;      // device
     SyncSummary *sy_summary_host = nullptr; // pinned
 
     uint64_t launches = 0;
@@ -265,8 +268,10 @@ int b200rx_destroy(b200rx_handle *h)
         if (i > 0) { cudaFree(l.desc); cudaFree(l.bm); cudaFree(l.dec); cudaFree(l.counters); }
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
-    cudaFree(h->sy_ev_x); cudaFree(h->sy_ev_count); cudaFree(h->sy_rec); cudaFree(h->sy_order); cudaFree(h->sy_lts1);
-    cudaFree(h->sy_avail); cudaFree(h->sy_rot); cudaFree(h->sy_phase); cudaFree(h->sy_summary);
+    for (auto &y : h->sy) {
+        cudaFree(y.ev_x); cudaFree(y.ev_count); cudaFree(y.rec); cudaFree(y.order); cudaFree(y.lts1);
+        cudaFree(y.avail); cudaFree(y.rot); cudaFree(y.phase); cudaFree(y.summary);
+    }
     if (h->sy_summary_host) cudaFreeHost(h->sy_summary_host);
     use_lane(h, 0);
     cudaFree(h->desc); cudaFree(h->bm); cudaFree(h->dec); cudaFree(h->counters);
@@ -381,7 +386,7 @@ struct OutPtrs { uint8_t *payload; uint32_t stride; uint16_t *len; uint8_t *rate
 // K1 -> K2 -> K3 for frames [off, off + n) of the batch on stream s; ev (4 events) optional.
 int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, const double *iq_dev, uint64_t iq_samples,
                  const uint64_t *lts1_dev, const uint32_t *avail_dev, const OutPtrs &o, const b200rx_debug *dbg,
-                 cudaEvent_t *ev, const FrameRot *rot_dev = nullptr)
+                 cudaEvent_t *ev, const FrameRot *rot_dev = nullptr, const uint32_t *n_live_dev = nullptr)
 {
     const size_t S = h->max_steps;
     FrontendArgs fa{};
@@ -396,6 +401,7 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
     fa.max_steps = h->max_steps;
     fa.max_len = h->limits.max_payload_bytes;
     fa.rot = rot_dev ? rot_dev + off : nullptr;
+    fa.n_live = n_live_dev;
     if (dbg) {
         fa.dbg_eq = dbg->equalized ? reinterpret_cast<double2 *>(dbg->equalized) + (size_t)off * dbg->eq_vectors * 48 : nullptr;
         fa.dbg_eq_vectors = dbg->eq_vectors;
@@ -591,47 +597,58 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
 
 namespace {
 
-int ensure_sync_scratch(b200rx_handle *h)
+int ensure_sync_scratch(b200rx_handle *h, int lane)
 {
-    if (h->sy_summary_host) return B200RX_OK;
     const size_t nf = h->limits.max_frames;
     h->sy_ev_cap = (uint32_t)(2 * nf + 64);
     cudaError_t e = cudaSuccess;
-    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    A((void **)&h->sy_ev_x, h->sy_ev_cap * sizeof(uint64_t));
-    A((void **)&h->sy_ev_count, sizeof(uint32_t));
-    A((void **)&h->sy_rec, h->sy_ev_cap * sizeof(SyncRec));
-    A((void **)&h->sy_order, h->sy_ev_cap * sizeof(uint32_t));
-    A((void **)&h->sy_lts1, nf * sizeof(uint64_t));
-    A((void **)&h->sy_avail, nf * sizeof(uint32_t));
-    A((void **)&h->sy_rot, nf * sizeof(FrameRot));
-    A((void **)&h->sy_phase, nf * sizeof(double));
-    A((void **)&h->sy_summary, sizeof(SyncSummary));
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->sy_summary_host, sizeof(SyncSummary), cudaHostAllocDefault);
+    if (!h->sy_summary_host) e = cudaHostAlloc((void **)&h->sy_summary_host, sizeof(SyncSummary), cudaHostAllocDefault);
+    b200rx_handle::SyncScratch &y = h->sy[lane];
+    if (e == cudaSuccess && !y.summary) {
+        auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+        A((void **)&y.ev_x, h->sy_ev_cap * sizeof(uint64_t));
+        A((void **)&y.ev_count, sizeof(uint32_t));
+        A((void **)&y.rec, h->sy_ev_cap * sizeof(SyncRec));
+        A((void **)&y.order, h->sy_ev_cap * sizeof(uint32_t));
+        A((void **)&y.lts1, nf * sizeof(uint64_t));
+        A((void **)&y.avail, nf * sizeof(uint32_t));
+        A((void **)&y.rot, nf * sizeof(FrameRot));
+        A((void **)&y.phase, nf * sizeof(double));
+        A((void **)&y.summary, sizeof(SyncSummary));
+    }
     if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "sync scratch", e);
     return B200RX_OK;
 }
 
-// detector + timing sync on stream s into the handle's scratch; returns with the summary on the host
-int run_sync(b200rx_handle *h, cudaStream_t s, const double *iq_dev, uint64_t n_samples, double phase_in, uint8_t *tags_dev)
+// detector + timing sync on stream s into scratch set `lane` (asynchronous)
+int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const double *iq_dev, uint64_t n_samples, double phase_in,
+                     uint8_t *tags_dev)
 {
-    int rc = ensure_sync_scratch(h);
+    int rc = ensure_sync_scratch(h, lane);
     if (rc != B200RX_OK) return rc;
+    const b200rx_handle::SyncScratch &y = h->sy[lane];
     SyncArgs a{};
     a.iq = reinterpret_cast<const double2 *>(iq_dev);
     a.n_samples = n_samples;
     a.rot_in = make_double2(cos(phase_in), sin(phase_in)); // timing_sync.cpp:124
     a.max_frames = h->limits.max_frames;
     a.tags = tags_dev;
-    a.ev_x = h->sy_ev_x; a.ev_count = h->sy_ev_count; a.ev_cap = h->sy_ev_cap;
-    a.rec = h->sy_rec; a.order = h->sy_order;
-    a.lts1 = h->sy_lts1; a.avail = h->sy_avail; a.rot = h->sy_rot; a.phase = h->sy_phase;
-    a.summary = h->sy_summary;
+    a.ev_x = y.ev_x; a.ev_count = y.ev_count; a.ev_cap = h->sy_ev_cap;
+    a.rec = y.rec; a.order = y.order;
+    a.lts1 = y.lts1; a.avail = y.avail; a.rot = y.rot; a.phase = y.phase;
+    a.summary = y.summary;
     CU(h, launch_sync(a, s));
-    h->launches += n_samples ? 3 : 1;
-    CU(h, cudaMemcpyAsync(h->sy_summary_host, h->sy_summary, sizeof(SyncSummary), cudaMemcpyDeviceToHost, s));
+    h->launches += n_samples ? 4 : 1;
+    return B200RX_OK;
+}
+
+// summary of scratch set `lane` to the host; returns when everything queued on s so far has finished
+int fetch_summary(b200rx_handle *h, cudaStream_t s, int lane, double phase_in, b200rx_sync_result *res)
+{
+    CU(h, cudaMemcpyAsync(h->sy_summary_host, h->sy[lane].summary, sizeof(SyncSummary), cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));
-    if (!h->sy_summary_host->phase_valid) h->sy_summary_host->last_phase = phase_in;
+    *res = *h->sy_summary_host;
+    if (!res->phase_valid) res->last_phase = phase_in;
     return B200RX_OK;
 }
 
@@ -656,14 +673,16 @@ int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, 
     int rc = drain_lanes(h);
     if (rc != B200RX_OK) return rc;
     cudaStream_t s = h->stream;
-    rc = run_sync(h, s, iq_dev, n_samples, phase_in, tags_dev);
+    rc = launch_sync_lane(h, s, 0, iq_dev, n_samples, phase_in, tags_dev);
     if (rc != B200RX_OK) return rc;
-    *res = *h->sy_summary_host;
+    rc = fetch_summary(h, s, 0, phase_in, res);
+    if (rc != B200RX_OK) return rc;
     const size_t nf = res->n_frames;
     if (nf) {
-        if (lts1_index_dev) CU(h, cudaMemcpyAsync(lts1_index_dev, h->sy_lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
-        if (avail_dev) CU(h, cudaMemcpyAsync(avail_dev, h->sy_avail, nf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-        if (phase_dev) CU(h, cudaMemcpyAsync(phase_dev, h->sy_phase, nf * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        const b200rx_handle::SyncScratch &y = h->sy[0];
+        if (lts1_index_dev) CU(h, cudaMemcpyAsync(lts1_index_dev, y.lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        if (avail_dev) CU(h, cudaMemcpyAsync(avail_dev, y.avail, nf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        if (phase_dev) CU(h, cudaMemcpyAsync(phase_dev, y.phase, nf * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CU(h, cudaStreamSynchronize(s));
     }
     return B200RX_OK;
@@ -671,26 +690,40 @@ int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, 
 
 int b200rx_receive_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
                        uint8_t *payload_out_dev, uint32_t payload_stride, uint16_t *payload_len_dev, uint8_t *rate_out_dev,
-                       uint8_t *status_dev, uint64_t *lts1_out_dev, b200rx_sync_result *res)
+                       uint8_t *status_dev, uint64_t *lts1_out_dev, uint32_t *n_frames_dev, b200rx_sync_result *res)
 {
     if (!h) return B200RX_E_ARG;
-    if ((!iq_dev && n_samples) || !status_dev || !res) return fail(h, B200RX_E_ARG, "b200rx_receive_dev: null argument");
+    if ((!iq_dev && n_samples) || !status_dev) return fail(h, B200RX_E_ARG, "b200rx_receive_dev: null argument");
     CU(h, cudaSetDevice(h->device));
-    int rc = drain_lanes(h);
-    if (rc != B200RX_OK) return rc;
     cudaStream_t s = h->stream;
-    cudaEvent_t *ev = call_events(h);
+    b200rx_handle::Lane *lane = nullptr;
+    int li = 0;
+    if (h->depth > 1) {
+        li = (int)(h->call_idx % h->depth);
+        lane = &h->lanes[li];
+        CU(h, cudaEventRecord(h->ev_in, h->stream)); // the caller's samples are ready at this point of its stream
+        CU(h, cudaStreamWaitEvent(lane->stream, h->ev_in, 0));
+        s = lane->stream;
+        use_lane(h, li);
+    }
+    const uint32_t mf = h->limits.max_frames;
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
-    rc = run_sync(h, s, iq_dev, n_samples, phase_in, nullptr);
+    int rc = launch_sync_lane(h, s, li, iq_dev, n_samples, phase_in, nullptr);
     if (rc != B200RX_OK) return rc;
-    *res = *h->sy_summary_host;
-    const uint32_t nf = res->n_frames;
-    if (nf == 0) return B200RX_OK;
-    if (lts1_out_dev) CU(h, cudaMemcpyAsync(lts1_out_dev, h->sy_lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    const b200rx_handle::SyncScratch &y = h->sy[li];
+    cudaEvent_t *ev = call_events(h);
     const OutPtrs o{payload_out_dev, payload_stride, payload_len_dev, rate_out_dev, status_dev};
-    rc = launch_range(h, s, 0, nf, iq_dev, n_samples, h->sy_lts1, h->sy_avail, o, nullptr, ev, h->sy_rot);
+    rc = launch_range(h, s, 0, mf, iq_dev, n_samples, y.lts1, y.avail, o, nullptr, ev, y.rot, &y.summary->n_frames);
     if (rc != B200RX_OK) return rc;
     if (ev == h->ev) h->ev_valid = true;
+    if (lts1_out_dev) CU(h, cudaMemcpyAsync(lts1_out_dev, y.lts1, (size_t)mf * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    if (n_frames_dev) CU(h, cudaMemcpyAsync(n_frames_dev, &y.summary->n_frames, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    if (lane) {
+        CU(h, cudaEventRecord(lane->done, s));
+        lane->used = true;
+    }
+    h->call_idx++;
+    if (res) return fetch_summary(h, s, li, phase_in, res);
     return B200RX_OK;
 }
 
@@ -719,8 +752,9 @@ int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, doubl
         h->d_payload_cap = pl_cap;
     }
     if (iq_bytes) CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    const int li = h->depth > 1 ? (int)(h->call_idx % h->depth) : 0; // scratch set the next call uses
     rc = b200rx_receive_dev(h, h->d_iq, n_samples, phase_in, payload_out ? h->d_payload : nullptr, payload_stride, h->d_len,
-                            h->d_rate, h->d_status, nullptr, res);
+                            h->d_rate, h->d_status, nullptr, nullptr, res);
     if (rc != B200RX_OK) return rc;
     const size_t nf = res->n_frames;
     if (nf) {
@@ -728,7 +762,7 @@ int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, doubl
         if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
         if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, nf, cudaMemcpyDeviceToHost, s));
         CU(h, cudaMemcpyAsync(status, h->d_status, nf, cudaMemcpyDeviceToHost, s));
-        if (lts1_out) CU(h, cudaMemcpyAsync(lts1_out, h->sy_lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        if (lts1_out) CU(h, cudaMemcpyAsync(lts1_out, h->sy[li].lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     }
     CU(h, cudaStreamSynchronize(s));
     return B200RX_OK;

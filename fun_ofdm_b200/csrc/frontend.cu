@@ -249,6 +249,15 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.n_live && (uint32_t)frame >= *a.n_live) { // slot without a frame (raw-capture entry points)
+        if (tid == 0) {
+            FrameDesc d;
+            d.n_steps = 0; d.data_bits = 0; d.field = 0; d.length = 0;
+            d.rate = B200RX_RATE_INVALID; d.status = B200RX_ST_NO_FRAME;
+            a.desc[frame] = d;
+        }
+        return;
+    }
     const uint64_t p = a.lts1[frame];
     uint32_t avail = a.avail[frame];
     if (p >= a.iq_samples) avail = 0;

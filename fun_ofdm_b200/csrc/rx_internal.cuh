@@ -147,6 +147,7 @@ struct FrontendArgs {
     uint32_t max_len;
     int header_only;         // 1: stop after the SIGNAL symbol (descriptor only, no branch metrics)
     const FrameRot *rot;     // per frame, or null: samples are used as they are
+    const uint32_t *n_live;  // device count of valid frames (slots beyond it become B200RX_ST_NO_FRAME), or null
     // taps (may be null)
     double2 *dbg_eq;
     uint32_t dbg_eq_vectors;

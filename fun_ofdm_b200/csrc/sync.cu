@@ -174,6 +174,26 @@ __global__ void __launch_bounds__(128) lts_sync_kernel(const double2 *iq, uint64
     }
 }
 
+// Rank of every event by stream position (x values are distinct: one tag per sample): order[rank] = event.
+__global__ void __launch_bounds__(256) rank_events_kernel(const SyncRec *rec, const uint32_t *ev_count, uint32_t ev_cap,
+                                                          uint32_t *order)
+{
+    __shared__ uint64_t s_x[256];
+    const uint32_t E = min(*ev_count, ev_cap);
+    const uint32_t e = blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.x * 256 >= E) return;
+    const uint64_t x = e < E ? rec[e].x : 0;
+    uint32_t rank = 0;
+    for (uint32_t base = 0; base < E; base += 256) {
+        __syncthreads();
+        s_x[threadIdx.x] = (base + threadIdx.x < E) ? rec[base + threadIdx.x].x : ~0ull;
+        __syncthreads();
+        const uint32_t m = min(256u, E - base);
+        for (uint32_t k = 0; k < m; k++) rank += s_x[k] < x;
+    }
+    if (e < E) order[rank] = e;
+}
+
 // Events -> frames in stream order (one CTA).  Frame k starts at the LTS1 tag of the k-th successful event;
 // it owns the samples up to the next LTS1 tag (fft_symbols.cpp:42-51 restarts there).
 constexpr int BF_THREADS = 1024;
@@ -188,14 +208,6 @@ __global__ void __launch_bounds__(BF_THREADS) build_frames_kernel(const SyncRec 
     const int tid = threadIdx.x;
     const uint32_t n_all = *ev_count;
     const uint32_t E = min(n_all, ev_cap);
-    // rank sort by x (x values are distinct: one tag per sample)
-    for (uint32_t e = tid; e < E; e += BF_THREADS) {
-        const uint64_t x = rec[e].x;
-        uint32_t rank = 0;
-        for (uint32_t k = 0; k < E; k++) rank += rec[k].x < x;
-        order[rank] = e;
-    }
-    __syncthreads();
     // is sorted event k the start of a new frame?  (found, and not the same LTS1 as the previous found event)
     auto is_frame = [&](uint32_t k) -> bool {
         const SyncRec &r = rec[order[k]];
@@ -298,7 +310,10 @@ cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s)
         detect_kernel<<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        lts_sync_kernel<<<592, 128, 0, s>>>(a.iq, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
+        lts_sync_kernel<<<a.ev_cap, 128, 0, s>>>(a.iq, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        rank_events_kernel<<<(a.ev_cap + 255) / 256, 256, 0, s>>>(a.rec, a.ev_count, a.ev_cap, a.order);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

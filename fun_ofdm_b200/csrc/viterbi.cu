@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
                 if (a.payload_len) a.payload_len[frame] = (d.status == B200RX_ST_TRUNCATED || d.status == B200RX_ST_TOO_LONG) ? d.length : 0;
                 if (a.rate_out) a.rate_out[frame] = d.rate;
                 if (a.dbg_field) a.dbg_field[frame] = d.field;
-                if (a.counters) atomicAdd(&a.counters[1], 1ull);
+                if (a.counters && d.status != B200RX_ST_NO_FRAME) atomicAdd(&a.counters[1], 1ull);
             }
             continue;
         }

@@ -5,6 +5,7 @@ import os
 import numpy as np
 
 ST_OK, ST_HDR_PARITY, ST_HDR_RATE, ST_CRC_FAIL, ST_TRUNCATED, ST_TOO_LONG = range(6)
+ST_NO_FRAME = 255
 RATE_INVALID = 255
 
 # fun::Rate -> (rate_field, cbps, dbps, bpsc)   reference src/rates.h:52-196
@@ -105,7 +106,7 @@ def load_library():
     L.b200rx_sync_dev.restype = C.c_int
     L.b200rx_sync_dev.argtypes = [vp, vp, u64, C.c_double, vp, vp, vp, vp, C.POINTER(SyncResult)]
     L.b200rx_receive_dev.restype = C.c_int
-    L.b200rx_receive_dev.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, C.POINTER(SyncResult)]
+    L.b200rx_receive_dev.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, vp, C.POINTER(SyncResult)]
     L.b200rx_receive.restype = C.c_int
     L.b200rx_receive.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, C.POINTER(SyncResult)]
     L.b200rx_viterbi_batch_dev.restype = C.c_int
@@ -277,16 +278,20 @@ class Receiver:
         self._check(rc, "b200rx_sync_dev")
         return res.as_dict()
 
-    def receive_dev(self, iq, payload, length, rate, status, lts1_index=None, phase_in=0.0):
+    def receive_dev(self, iq, payload, length, rate, status, lts1_index=None, phase_in=0.0, n_frames=None,
+                    wait=True):
         """Raw samples (CUDA tensor) -> payloads of the frames found, in stream order.  Output tensors are sized for
-        max_frames; entries [0, n_frames) are valid after synchronize().  Returns the summary dict."""
+        max_frames; slots beyond the frames found get status ST_NO_FRAME.  wait=True: returns the summary dict once
+        the outputs are complete.  wait=False: asynchronous (pipelined over the lanes of set_pipeline_depth); the
+        number of frames lands in the optional int32 [1] CUDA tensor `n_frames`."""
         n = int(iq.numel() if iq.is_complex() else iq.numel() // 2)
         res = SyncResult()
         rc = self.lib.b200rx_receive_dev(self.h, _ptr(iq), n, float(phase_in), _ptr(payload),
                                          int(payload.shape[1]) if payload is not None else 0, _ptr(length), _ptr(rate),
-                                         _ptr(status), _ptr(lts1_index), C.byref(res))
+                                         _ptr(status), _ptr(lts1_index), _ptr(n_frames),
+                                         C.byref(res) if wait else None)
         self._check(rc, "b200rx_receive_dev")
-        return res.as_dict()
+        return res.as_dict() if wait else None
 
     def receive(self, samples, phase_in=0.0):
         """Host samples (complex128 array) -> (list of payload bytes of CRC-OK frames in stream order, info dict with

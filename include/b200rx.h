@@ -45,6 +45,7 @@ extern "C" {
 #define B200RX_ST_CRC_FAIL 3    /* CRC-32 mismatch (ppdu.cpp:274-279) */
 #define B200RX_ST_TRUNCATED 4   /* fewer samples than 128 + 80*(1 + nsym) were supplied for the frame */
 #define B200RX_ST_TOO_LONG 5    /* decoded LENGTH exceeds the handle's max_payload_bytes */
+#define B200RX_ST_NO_FRAME 255  /* b200rx_receive*: output slot beyond the number of frames found in the capture */
 
 /* ---- fun::Rate enum values (reference src/rates.h:31-44), as written to rate_out ---- */
 #define B200RX_RATE_1_2_BPSK 0
@@ -178,13 +179,16 @@ B200RX_API int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t 
                                uint8_t *tags_dev, uint64_t *lts1_index_dev, uint32_t *avail_dev, double *phase_dev,
                                b200rx_sync_result *res);
 
-/* Raw samples in HBM -> payloads: detection, synchronisation, phase rotation and the hot path.  Outputs are
- * device arrays sized for max_frames; entries [0, res->n_frames) are valid once the handle's stream has been
- * synchronised.  lts1_out_dev (nullable) receives the LTS1 index of every frame. */
+/* Raw samples in HBM -> payloads: detection, synchronisation, phase rotation and the hot path, with no host
+ * round trip in between (the decode kernels are launched for max_frames slots and read the number of frames
+ * found from device memory).  Outputs are device arrays sized for max_frames: slots [0, n_frames) hold the frames
+ * in stream order, the rest get status B200RX_ST_NO_FRAME.  lts1_out_dev [max_frames] and n_frames_dev [1] are
+ * optional.  res != NULL: the call returns when the summary is on the host (outputs complete).  res == NULL: fully
+ * asynchronous, pipelined over the lanes of b200rx_set_pipeline_depth like b200rx_decode_batch_dev. */
 B200RX_API int b200rx_receive_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
                                   uint8_t *payload_out_dev, uint32_t payload_stride, uint16_t *payload_len_dev,
                                   uint8_t *rate_out_dev, uint8_t *status_dev, uint64_t *lts1_out_dev,
-                                  b200rx_sync_result *res);
+                                  uint32_t *n_frames_dev, b200rx_sync_result *res);
 
 /* Same with host buffers (pinned buffers recommended); synchronous. */
 B200RX_API int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, double phase_in,

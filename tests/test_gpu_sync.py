@@ -133,6 +133,51 @@ def test_receive_matches_reference_chain(ref, rx_factory, snr):
     assert np.array_equal(st, info["status"]) and np.array_equal(lts1.cpu().numpy()[:nf].astype(np.uint64), info["lts1"])
 
 
+def test_pipelined_receive_equals_synchronous(ref, rx_factory):
+    """Asynchronous b200rx_receive_dev calls rotating over pipeline lanes give what the synchronous call gives."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    caps = [_capture(ref, rng, [10, 8, 3, 0, 5][: 2 + k], [900, 40, 300, 10, 1500][: 2 + k], 26)[0] for k in range(4)]
+    rx = rx_factory(32, 1500)
+    mf = rx.max_frames
+
+    def outs():
+        return dict(payload=torch.zeros((mf, 1500), dtype=torch.uint8, device=dev),
+                    length=torch.zeros(mf, dtype=torch.int16, device=dev), rate=torch.zeros(mf, dtype=torch.uint8, device=dev),
+                    status=torch.zeros(mf, dtype=torch.uint8, device=dev), lts1=torch.zeros(mf, dtype=torch.int64, device=dev),
+                    n=torch.zeros(1, dtype=torch.int32, device=dev))
+
+    d = [torch.from_numpy(np.ascontiguousarray(c).view(np.float64)).to(dev) for c in caps]
+    want = []
+    for k in range(4):
+        o = outs()
+        res = rx.receive_dev(d[k], o["payload"], o["length"], o["rate"], o["status"], o["lts1"])
+        rx.synchronize()
+        ref_tags, _ = _ref_tags(ref, caps[k])
+        n_ref = int(np.count_nonzero(ref_tags[: len(caps[k]) - DELAY] == TAG_LTS1))
+        assert res["n_frames"] == n_ref >= 2 + k  # (the reference tags the odd spurious LTS as well)
+        want.append(dict({key: v.cpu().numpy().copy() for key, v in o.items()}, nf=n_ref))
+        assert (want[-1]["status"][n_ref:] == 255).all() and (want[-1]["status"][:n_ref] != 255).all()
+    rx.set_pipeline_depth(3)
+    got = [outs() for _ in range(4)]
+    for rep in range(2):
+        for k in range(4):
+            o = got[k]
+            rx.receive_dev(d[k], o["payload"], o["length"], o["rate"], o["status"], o["lts1"], n_frames=o["n"], wait=False)
+            if k == 2:
+                rx.join(2)  # call 0 of this round is complete from here on (on the handle's stream)
+    rx.join(0)
+    rx.synchronize()
+    for k in range(4):
+        nf = int(got[k]["n"].item())
+        assert nf == want[k]["nf"]
+        for key in ("payload", "length", "rate", "status"):
+            assert np.array_equal(got[k][key].cpu().numpy(), want[k][key]), (k, key)
+        assert np.array_equal(got[k]["lts1"].cpu().numpy()[:nf], want[k]["lts1"][:nf])
+    rx.set_pipeline_depth(1)
+
+
 def test_rotation_carries_over_between_captures(ref, rx_factory):
     """phase_in: the phase a previous capture left behind rotates the samples before the first STS_END."""
     rng = np.random.default_rng(9)
