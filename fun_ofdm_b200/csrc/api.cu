@@ -35,7 +35,7 @@ struct b200rx_handle {
     unsigned long long *counters = nullptr; // 8 words (5 used)
 
     // staging for the host-buffer entry point (grow-only)
-    double *d_iq = nullptr; size_t d_iq_cap = 0;
+    uint8_t *d_iq = nullptr; size_t d_iq_cap = 0; // bytes, samples in the handle's format
     uint64_t *d_lts1 = nullptr;
     uint32_t *d_avail = nullptr;
     uint8_t *d_payload = nullptr; size_t d_payload_cap = 0;
@@ -73,6 +73,11 @@ struct b200rx_handle {
     SyncScratch sy[B200RX_MAX_PIPELINE_DEPTH];
     uint32_t sy_ev_cap = 0;
     SyncSummary *sy_summary_host = nullptr; // pinned
+
+    // format of every `iq` argument (b200rx_set_sample_format)
+    int fmt = FMT_FC64;
+    double scale = 1.0;
+    int sm_count = 148;
 
     uint64_t launches = 0;
     std::string error;
@@ -224,6 +229,7 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     b200rx_handle *h = new (std::nothrow) b200rx_handle();
     if (!h) return fail(nullptr, B200RX_E_NOMEM, "b200rx_create: out of host memory");
     h->device = device;
+    h->sm_count = prop.multiProcessorCount;
     h->limits = *limits;
     h->max_steps = max_steps_for(limits->max_payload_bytes);
     const size_t nf = limits->max_frames;
@@ -293,6 +299,17 @@ int b200rx_set_stream(b200rx_handle *h, void *cuda_stream)
 {
     if (!h) return B200RX_E_ARG;
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return B200RX_OK;
+}
+
+int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale)
+{
+    if (!h) return B200RX_E_ARG;
+    if (format != B200RX_FMT_FC64 && format != B200RX_FMT_FC32 && format != B200RX_FMT_SC16)
+        return fail(h, B200RX_E_ARG, "b200rx_set_sample_format: unknown format");
+    if (format == B200RX_FMT_SC16 && !(sc16_scale > 0.0)) return fail(h, B200RX_E_ARG, "b200rx_set_sample_format: scale must be > 0");
+    h->fmt = format;
+    h->scale = format == B200RX_FMT_SC16 ? sc16_scale : 1.0;
     return B200RX_OK;
 }
 
@@ -384,13 +401,15 @@ namespace {
 struct OutPtrs { uint8_t *payload; uint32_t stride; uint16_t *len; uint8_t *rate; uint8_t *status; };
 
 // K1 -> K2 -> K3 for frames [off, off + n) of the batch on stream s; ev (4 events) optional.
-int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, const double *iq_dev, uint64_t iq_samples,
+int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, const void *iq_dev, uint64_t iq_samples,
                  const uint64_t *lts1_dev, const uint32_t *avail_dev, const OutPtrs &o, const b200rx_debug *dbg,
                  cudaEvent_t *ev, const FrameRot *rot_dev = nullptr, const uint32_t *n_live_dev = nullptr)
 {
     const size_t S = h->max_steps;
     FrontendArgs fa{};
-    fa.iq = reinterpret_cast<const double2 *>(iq_dev);
+    fa.iq = iq_dev;
+    fa.fmt = h->fmt;
+    fa.scale = h->scale;
     fa.iq_samples = iq_samples;
     fa.lts1 = lts1_dev + off;
     fa.avail = avail_dev + off;
@@ -439,7 +458,7 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
 
 } // namespace
 
-int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_samples,
+int b200rx_decode_batch_dev(b200rx_handle *h, const void *iq_dev, uint64_t iq_samples,
                             const uint64_t *lts1_index_dev, const uint32_t *avail_dev, uint32_t n_frames,
                             uint8_t *payload_out_dev, uint32_t payload_stride,
                             uint16_t *payload_len_dev, uint8_t *rate_out_dev, uint8_t *status_dev,
@@ -475,7 +494,7 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_
     return B200RX_OK;
 }
 
-int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
+int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
                         const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
                         uint8_t *payload_out, uint32_t payload_stride,
                         uint16_t *payload_len, uint8_t *rate_out, uint8_t *status)
@@ -492,7 +511,8 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
 
-    const size_t iq_bytes = (size_t)iq_samples * 2 * sizeof(double);
+    const size_t bps = sample_bytes(h->fmt);
+    const size_t iq_bytes = (size_t)iq_samples * bps;
     if (iq_bytes > h->d_iq_cap) {
         if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
         cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
@@ -526,6 +546,17 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
         long v = e ? atol(e) : 0;
         return (uint32_t)(v >= 16 ? v : 64);
     }();
+    // Pinned caller buffer: the GPU pulls the useful samples itself (ingest.cu) instead of a DMA copy of everything.
+    const char *pull_env = getenv("B200RX_PULL"); // B200RX_PULL=0: always DMA-copy (for A/B measurements)
+    const bool PULL = !(pull_env && atoi(pull_env) == 0);
+    const void *iq_mapped = nullptr;
+    if (PULL) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, iq) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            iq_mapped = at.devicePointer;
+        else
+            (void)cudaGetLastError();
+    }
     bool ordered = n_frames > 2 * CH_MIN;
     for (uint32_t f = 1; ordered && f < n_frames; f++) ordered = lts1_index[f] >= lts1_index[f - 1];
     if (!ordered) {
@@ -568,8 +599,12 @@ int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
         }
         uint64_t lo = lts1_index[f0] < iq_samples ? lts1_index[f0] : iq_samples;
         if (lo < copied) lo = copied;
-        if (hi > lo) {
-            CU(h, cudaMemcpyAsync(h->d_iq + 2 * lo, iq + 2 * lo, (size_t)(hi - lo) * 2 * sizeof(double),
+        if (iq_mapped) {
+            CU(h, launch_pull(iq_mapped, h->d_iq, h->fmt, iq_samples, h->d_lts1 + f0, h->d_avail + f0, f1 - f0, h->sm_count,
+                              h->copy_stream));
+            h->launches++;
+        } else if (hi > lo) {
+            CU(h, cudaMemcpyAsync(h->d_iq + lo * bps, (const uint8_t *)iq + lo * bps, (size_t)(hi - lo) * bps,
                                   cudaMemcpyHostToDevice, h->copy_stream));
             copied = hi;
         }
@@ -621,14 +656,16 @@ int ensure_sync_scratch(b200rx_handle *h, int lane)
 }
 
 // detector + timing sync on stream s into scratch set `lane` (asynchronous)
-int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const double *iq_dev, uint64_t n_samples, double phase_in,
+int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const void *iq_dev, uint64_t n_samples, double phase_in,
                      uint8_t *tags_dev)
 {
     int rc = ensure_sync_scratch(h, lane);
     if (rc != B200RX_OK) return rc;
     const b200rx_handle::SyncScratch &y = h->sy[lane];
     SyncArgs a{};
-    a.iq = reinterpret_cast<const double2 *>(iq_dev);
+    a.iq = iq_dev;
+    a.fmt = h->fmt;
+    a.scale = h->scale;
     a.n_samples = n_samples;
     a.rot_in = make_double2(cos(phase_in), sin(phase_in)); // timing_sync.cpp:124
     a.max_frames = h->limits.max_frames;
@@ -664,7 +701,7 @@ int drain_lanes(b200rx_handle *h)
 
 } // namespace
 
-int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in, uint8_t *tags_dev,
+int b200rx_sync_dev(b200rx_handle *h, const void *iq_dev, uint64_t n_samples, double phase_in, uint8_t *tags_dev,
                     uint64_t *lts1_index_dev, uint32_t *avail_dev, double *phase_dev, b200rx_sync_result *res)
 {
     if (!h) return B200RX_E_ARG;
@@ -688,7 +725,7 @@ int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, 
     return B200RX_OK;
 }
 
-int b200rx_receive_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
+int b200rx_receive_dev(b200rx_handle *h, const void *iq_dev, uint64_t n_samples, double phase_in,
                        uint8_t *payload_out_dev, uint32_t payload_stride, uint16_t *payload_len_dev, uint8_t *rate_out_dev,
                        uint8_t *status_dev, uint64_t *lts1_out_dev, uint32_t *n_frames_dev, b200rx_sync_result *res)
 {
@@ -727,7 +764,7 @@ int b200rx_receive_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_sample
     return B200RX_OK;
 }
 
-int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, double phase_in, uint8_t *payload_out,
+int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n_samples, double phase_in, uint8_t *payload_out,
                    uint32_t payload_stride, uint16_t *payload_len, uint8_t *rate_out, uint8_t *status, uint64_t *lts1_out,
                    b200rx_sync_result *res)
 {
@@ -737,7 +774,7 @@ int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, doubl
     int rc = drain_lanes(h);
     if (rc != B200RX_OK) return rc;
     cudaStream_t s = h->stream;
-    const size_t iq_bytes = (size_t)n_samples * 2 * sizeof(double);
+    const size_t iq_bytes = (size_t)n_samples * sample_bytes(h->fmt);
     if (iq_bytes > h->d_iq_cap) {
         if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
         cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
@@ -768,7 +805,7 @@ int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, doubl
     return B200RX_OK;
 }
 
-int b200rx_decode_headers(b200rx_handle *h, const double *iq, uint64_t iq_samples, const uint64_t *lts1_index,
+int b200rx_decode_headers(b200rx_handle *h, const void *iq, uint64_t iq_samples, const uint64_t *lts1_index,
                           const uint32_t *avail, uint32_t n_frames, uint16_t *payload_len, uint8_t *rate_out,
                           uint8_t *status)
 {
@@ -783,7 +820,7 @@ int b200rx_decode_headers(b200rx_handle *h, const double *iq, uint64_t iq_sample
     }
     CU(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    const size_t iq_bytes = (size_t)iq_samples * 2 * sizeof(double);
+    const size_t iq_bytes = (size_t)iq_samples * sample_bytes(h->fmt);
     if (iq_bytes > h->d_iq_cap) {
         if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
         cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
@@ -794,7 +831,9 @@ int b200rx_decode_headers(b200rx_handle *h, const double *iq, uint64_t iq_sample
     CU(h, cudaMemcpyAsync(h->d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CU(h, cudaMemcpyAsync(h->d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     FrontendArgs fa{};
-    fa.iq = reinterpret_cast<const double2 *>(h->d_iq);
+    fa.iq = h->d_iq;
+    fa.fmt = h->fmt;
+    fa.scale = h->scale;
     fa.iq_samples = iq_samples;
     fa.lts1 = h->d_lts1;
     fa.avail = h->d_avail;

@@ -169,10 +169,17 @@ struct RotCtx {
     int64_t from;    // relative to the frame's LTS1
 };
 
-template <bool ROT>
-__device__ __forceinline__ double2 fetch(const double2 *win, int k, const RotCtx &rc)
+// The samples of one frame: `base` in format FMT, the frame's LTS1 tag at sample index `p`.
+struct Window {
+    const void *base;
+    uint64_t p;
+    double scale;
+};
+
+template <bool ROT, int FMT>
+__device__ __forceinline__ double2 fetch(const Window &win, int k, const RotCtx &rc)
 {
-    double2 v = win[k];
+    double2 v = load_sample<FMT>(win.base, win.p + (uint64_t)k, win.scale);
     if constexpr (ROT) {
         const double2 r = ((int64_t)k >= rc.from) ? rc.rn : rc.ro;
         v = make_double2(__dsub_rn(__dmul_rn(v.x, r.x), __dmul_rn(v.y, r.y)),
@@ -190,11 +197,11 @@ struct SymbolCtx {
 
 // One OFDM symbol: samples -> equalised, derotated data carriers -> soft bits in ctx.soft.
 // v = symbol index from SIGNAL (0) on: selects the pilot polarity (phase_tracker.cpp:77-86).
-template <bool ROT>
-__device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const double2 *win, int off, const RotCtx &rc, int v,
+template <bool ROT, int FMT>
+__device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const Window &win, int off, const RotCtx &rc, int v,
                                                int bpsc, int lane, double2 *dbg_eq)
 {
-    double2 v0 = fetch<ROT>(win, off + lane, rc), v1 = fetch<ROT>(win, off + lane + 32, rc);
+    double2 v0 = fetch<ROT, FMT>(win, off + lane, rc), v1 = fetch<ROT, FMT>(win, off + lane + 32, rc);
     warp_fft64(v0, v1, ctx.tw, lane);
     ctx.xs[shifted_index(lane, 0)] = v0;
     ctx.xs[shifted_index(lane, 1)] = v1;
@@ -236,7 +243,7 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const doubl
     __syncwarp();
 }
 
-template <bool ROT>
+template <bool ROT, int FMT>
 __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 {
     __shared__ double2 s_tw[64];
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     uint32_t avail = a.avail[frame];
     if (p >= a.iq_samples) avail = 0;
     else if ((uint64_t)avail > a.iq_samples - p) avail = (uint32_t)(a.iq_samples - p);
-    const double2 *win = a.iq + p;
+    const Window win{a.iq, p, a.scale};
     RotCtx rc{};
     if constexpr (ROT) {
         const FrameRot fr = a.rot[frame];
@@ -290,7 +297,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 
     // ---- channel estimate: channel_est.cpp:53-58, H^-1[j] = sum_{2 LTS} L[j] / R[j] / 2 for all 64 bins ----
     if (warp < 2) {
-        double2 v0 = fetch<ROT>(win, 64 * warp + lane, rc), v1 = fetch<ROT>(win, 64 * warp + lane + 32, rc);
+        double2 v0 = fetch<ROT, FMT>(win, 64 * warp + lane, rc), v1 = fetch<ROT, FMT>(win, 64 * warp + lane + 32, rc);
         warp_fft64(v0, v1, s_tw, lane);
 #pragma unroll
         for (int slot = 0; slot < 2; slot++) {
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     // ---- SIGNAL: ppdu.cpp:168-218 ----
     if (warp == 0) {
         double2 *dbg = a.dbg_eq ? a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors) * 48 : nullptr;
-        process_symbol<ROT>(ctx, win, 128 + 16, rc, 0, 1, lane, (dbg && a.dbg_eq_vectors > 0) ? dbg : nullptr);
+        process_symbol<ROT, FMT>(ctx, win, 128 + 16, rc, 0, 1, lane, (dbg && a.dbg_eq_vectors > 0) ? dbg : nullptr);
         if (lane < 24) {
             uint32_t s0, s1;
             step_symbols(ctx.soft, PUNC_1_2, lane, s0, s1);
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     for (uint32_t s = warp; s < nsym; s += FE_WARPS) {
         double2 *dbg = nullptr;
         if (a.dbg_eq && s + 1 < a.dbg_eq_vectors) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors + s + 1) * 48;
-        process_symbol<ROT>(ctx, win, 128 + 80 * (int)(s + 1) + 16, rc, (int)(s + 1), rr.bpsc, lane, dbg);
+        process_symbol<ROT, FMT>(ctx, win, 128 + 80 * (int)(s + 1) + 16, rc, (int)(s + 1), rr.bpsc, lane, dbg);
         uint32_t *sym_out = bm_out + (size_t)s * rr.dbps;
         for (int t = lane; t < rr.dbps; t += 32) {
             const uint32_t pair = s_idx[t];
@@ -391,8 +398,16 @@ cudaError_t upload_frontend_tables(const double2 *tw, const int8_t *pol)
 cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s)
 {
     if (a.n_frames == 0) return cudaSuccess;
-    if (a.rot) frontend_kernel<true><<<a.n_frames, FE_WARPS * 32, 0, s>>>(a);
-    else frontend_kernel<false><<<a.n_frames, FE_WARPS * 32, 0, s>>>(a);
+    const dim3 grid(a.n_frames), block(FE_WARPS * 32);
+    switch (a.fmt * 2 + (a.rot ? 1 : 0)) {
+        case FMT_FC64 * 2: frontend_kernel<false, FMT_FC64><<<grid, block, 0, s>>>(a); break;
+        case FMT_FC64 * 2 + 1: frontend_kernel<true, FMT_FC64><<<grid, block, 0, s>>>(a); break;
+        case FMT_FC32 * 2: frontend_kernel<false, FMT_FC32><<<grid, block, 0, s>>>(a); break;
+        case FMT_FC32 * 2 + 1: frontend_kernel<true, FMT_FC32><<<grid, block, 0, s>>>(a); break;
+        case FMT_SC16 * 2: frontend_kernel<false, FMT_SC16><<<grid, block, 0, s>>>(a); break;
+        case FMT_SC16 * 2 + 1: frontend_kernel<true, FMT_SC16><<<grid, block, 0, s>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -95,6 +95,31 @@ __host__ __device__ __forceinline__ uint32_t branch_class(uint32_t j)
     return (b0 << 1) | b1;
 }
 
+// ---- sample formats of the ingest side (b200rx_set_sample_format) ----
+// FC64 is the reference's own std::complex<double> (tagged_vector.h:82-94, usrp.cpp:43 cpu format "fc64"); FC32 and SC16
+// are the narrower formats the same samples have on the radio side (usrp.cpp:44 wire format "sc16").  The widening to
+// double happens in the load, exactly (float -> double) or with one rounding ((double)int16 * scale), so the kernels
+// compute what the reference computes when it is handed the widened samples.
+enum { FMT_FC64 = B200RX_FMT_FC64, FMT_FC32 = B200RX_FMT_FC32, FMT_SC16 = B200RX_FMT_SC16 };
+
+__host__ __device__ __forceinline__ size_t sample_bytes(int fmt) { return fmt == FMT_FC64 ? 16 : (fmt == FMT_FC32 ? 8 : 4); }
+
+#ifdef __CUDACC__
+template <int FMT>
+__device__ __forceinline__ double2 load_sample(const void *base, uint64_t i, double scale)
+{
+    if constexpr (FMT == FMT_FC64) {
+        return reinterpret_cast<const double2 *>(base)[i];
+    } else if constexpr (FMT == FMT_FC32) {
+        const float2 v = reinterpret_cast<const float2 *>(base)[i];
+        return make_double2((double)v.x, (double)v.y);
+    } else {
+        const short2 v = reinterpret_cast<const short2 *>(base)[i];
+        return make_double2(__dmul_rn((double)v.x, scale), __dmul_rn((double)v.y, scale));
+    }
+}
+#endif
+
 // ---- frame detection / timing synchronisation (sync.cu) ----
 struct SyncRec {      // outcome of one STS_END event (timing_sync.cpp:71-118)
     uint64_t x;       // stream index of the STS_END tag
@@ -113,7 +138,9 @@ struct FrameRot {     // constant rotation timing_sync applies to the samples of
 typedef b200rx_sync_result SyncSummary;
 
 struct SyncArgs {
-    const double2 *iq;
+    const void *iq;       // samples in format `fmt`
+    int fmt;
+    double scale;         // FMT_SC16: value of one LSB
     uint64_t n_samples;
     double2 rot_in;       // (cos, sin) of m_phase_acc before the stream
     uint32_t max_frames;
@@ -135,7 +162,9 @@ cudaError_t upload_sync_tables();
 
 // ---- launchers (each returns the cudaError_t of the launch) ----
 struct FrontendArgs {
-    const double2 *iq;
+    const void *iq;          // samples in format `fmt`
+    int fmt;
+    double scale;            // FMT_SC16: value of one LSB
     uint64_t iq_samples;
     const uint64_t *lts1;
     const uint32_t *avail;
@@ -185,6 +214,9 @@ cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s);
 
 cudaError_t launch_export_headers(const FrameDesc *desc, uint32_t n, uint16_t *len, uint8_t *rate, uint8_t *status,
                                   cudaStream_t s);
+
+cudaError_t launch_pull(const void *src, void *dst, int fmt, uint64_t n_samples, const uint64_t *lts1, const uint32_t *avail,
+                        uint32_t n_frames, int sm_count, cudaStream_t s);
 
 cudaError_t upload_tables();
 

@@ -40,8 +40,10 @@ constexpr double LTS_CORR_THRESHOLD = 0.9; // timing_sync.h:12
 
 enum : uint8_t { TAG_NONE = 0, TAG_STS_START = 1, TAG_STS_END = 2, TAG_LTS1 = 4, TAG_LTS2 = 5 }; // tagged_vector.h:25-34
 
-__global__ void __launch_bounds__(DET_THREADS) detect_kernel(const double2 *iq, uint64_t n, uint8_t *tags, uint64_t *ev_x,
-                                                             uint32_t *ev_count, uint32_t ev_cap, uint64_t x_limit)
+template <int FMT>
+__global__ void __launch_bounds__(DET_THREADS) detect_kernel(const void *iq, double scale, uint64_t n, uint8_t *tags,
+                                                             uint64_t *ev_x, uint32_t *ev_count, uint32_t ev_cap,
+                                                             uint64_t x_limit)
 {
     __shared__ double2 s_s[DT + 48];
     __shared__ double2 s_c[DT + 32];
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(DET_THREADS) detect_kernel(const double2 *iq, 
 
     for (int k = tid; k < DT + 48; k += DET_THREADS) {
         const int64_t i = t0 - 48 + k;
-        s_s[k] = (i >= 0 && (uint64_t)i < n) ? iq[i] : make_double2(0.0, 0.0); // the carry-over starts as zeros (frame_detector.cpp:27)
+        s_s[k] = (i >= 0 && (uint64_t)i < n) ? load_sample<FMT>(iq, (uint64_t)i, scale) : make_double2(0.0, 0.0); // the carry-over starts as zeros (frame_detector.cpp:27)
     }
     __syncthreads();
     // products of stream index t0 - 32 + j
@@ -101,7 +103,8 @@ __global__ void __launch_bounds__(DET_THREADS) detect_kernel(const double2 *iq, 
 
 // One CTA per STS_END event: 96 candidate offsets, 64 taps each (timing_sync.cpp:74-87), then the peak logic
 // (timing_sync.cpp:89-118) on one thread.
-__global__ void __launch_bounds__(128) lts_sync_kernel(const double2 *iq, uint64_t n, const uint64_t *ev_x,
+template <int FMT>
+__global__ void __launch_bounds__(128) lts_sync_kernel(const void *iq, double scale, uint64_t n, const uint64_t *ev_x,
                                                        const uint32_t *ev_count, uint32_t ev_cap, SyncRec *rec)
 {
     __shared__ double2 s_s[160];
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(128) lts_sync_kernel(const double2 *iq, uint64
     for (uint32_t e = blockIdx.x; e < n_ev; e += gridDim.x) {
         const uint64_t x = ev_x[e];
         __syncthreads();
-        for (int k = tid; k < 160; k += 128) s_s[k] = (x + k < n) ? iq[x + k] : make_double2(0.0, 0.0);
+        for (int k = tid; k < 160; k += 128) s_s[k] = (x + k < n) ? load_sample<FMT>(iq, x + k, scale) : make_double2(0.0, 0.0);
         __syncthreads();
         if (tid < 96) {
             double cr = 0.0, ci = 0.0, pw = 0.0;
@@ -307,10 +310,21 @@ cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s)
     if (a.n_samples > 0) {
         const uint64_t blocks = (a.n_samples + DT - 1) / DT;
         const uint64_t x_limit = a.n_samples > 160 ? a.n_samples - 160 : 0; // timing_sync.cpp:68: x < input.size() - CARRYOVER_LENGTH
-        detect_kernel<<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        lts_sync_kernel<<<a.ev_cap, 128, 0, s>>>(a.iq, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
+        switch (a.fmt) {
+            case FMT_FC64:
+                detect_kernel<FMT_FC64><<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
+                lts_sync_kernel<FMT_FC64><<<a.ev_cap, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
+                break;
+            case FMT_FC32:
+                detect_kernel<FMT_FC32><<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
+                lts_sync_kernel<FMT_FC32><<<a.ev_cap, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
+                break;
+            case FMT_SC16:
+                detect_kernel<FMT_SC16><<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
+                lts_sync_kernel<FMT_SC16><<<a.ev_cap, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
+                break;
+            default: return cudaErrorInvalidValue;
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         rank_events_kernel<<<(a.ev_cap + 255) / 256, 256, 0, s>>>(a.rec, a.ev_count, a.ev_cap, a.order);

@@ -7,6 +7,8 @@ import numpy as np
 ST_OK, ST_HDR_PARITY, ST_HDR_RATE, ST_CRC_FAIL, ST_TRUNCATED, ST_TOO_LONG = range(6)
 ST_NO_FRAME = 255
 RATE_INVALID = 255
+FMT_FC64, FMT_FC32, FMT_SC16 = 0, 1, 2
+_FMT_BYTES = {FMT_FC64: 16, FMT_FC32: 8, FMT_SC16: 4}
 
 # fun::Rate -> (rate_field, cbps, dbps, bpsc)   reference src/rates.h:52-196
 RATE_PARAMS = {
@@ -89,6 +91,8 @@ def load_library():
     L.b200rx_set_stream.argtypes = [vp, vp]
     L.b200rx_synchronize.restype = C.c_int
     L.b200rx_synchronize.argtypes = [vp]
+    L.b200rx_set_sample_format.restype = C.c_int
+    L.b200rx_set_sample_format.argtypes = [vp, C.c_int, C.c_double]
     L.b200rx_set_pipeline_depth.restype = C.c_int
     L.b200rx_set_pipeline_depth.argtypes = [vp, u32]
     L.b200rx_join.restype = C.c_int
@@ -146,6 +150,23 @@ class Receiver:
         if rc != 0:
             raise B200RxError("b200rx_create failed (%d): %s" % (rc, self.lib.b200rx_last_error(None).decode()))
         self.h = h
+        self.fmt = FMT_FC64
+
+    def set_sample_format(self, fmt, sc16_scale=1.0):
+        """FMT_FC64 (default), FMT_FC32 (float32 re, im) or FMT_SC16 (int16 re, im; sample = int16 * sc16_scale)."""
+        self._check(self.lib.b200rx_set_sample_format(self.h, int(fmt), float(sc16_scale)), "b200rx_set_sample_format")
+        self.fmt = int(fmt)
+
+    def _host_samples(self, iq):
+        """numpy array in the handle's format -> (contiguous array, number of complex samples)"""
+        iq = np.ascontiguousarray(iq)
+        want = {FMT_FC64: (np.complex128, np.float64), FMT_FC32: (np.complex64, np.float32), FMT_SC16: (np.int16, np.int16)}[self.fmt]
+        if iq.dtype not in want:
+            raise B200RxError("samples of dtype %s do not match the handle's sample format %d" % (iq.dtype, self.fmt))
+        return iq, iq.nbytes // _FMT_BYTES[self.fmt]
+
+    def _dev_samples(self, iq):
+        return int(iq.numel() * iq.element_size()) // _FMT_BYTES[self.fmt]
 
     def close(self):
         if getattr(self, "h", None):
@@ -215,10 +236,7 @@ class Receiver:
     def decode_batch(self, iq, lts1_index, avail, payload_stride=None):
         """iq: complex128 or float64 (re, im interleaved) numpy array.  Returns
         (payload[n, stride] u8, length[n] u16, rate[n] u8, status[n] u8)."""
-        iq = np.ascontiguousarray(iq)
-        if iq.dtype == np.complex128:
-            iq = iq.view(np.float64)
-        assert iq.dtype == np.float64
+        iq, iq_samples = self._host_samples(iq)
         lts1 = np.ascontiguousarray(lts1_index, dtype=np.uint64)
         av = np.ascontiguousarray(avail, dtype=np.uint32)
         n = len(lts1)
@@ -227,7 +245,7 @@ class Receiver:
         length = np.zeros(n, dtype=np.uint16)
         rate = np.zeros(n, dtype=np.uint8)
         status = np.zeros(n, dtype=np.uint8)
-        rc = self.lib.b200rx_decode_batch(self.h, iq.ctypes.data, iq.size // 2, lts1.ctypes.data, av.ctypes.data, n,
+        rc = self.lib.b200rx_decode_batch(self.h, iq.ctypes.data, iq_samples, lts1.ctypes.data, av.ctypes.data, n,
                                           payload.ctypes.data, stride, length.ctypes.data, rate.ctypes.data,
                                           status.ctypes.data)
         self._check(rc, "b200rx_decode_batch")
@@ -246,7 +264,7 @@ class Receiver:
         [n], avail int32 [n], payload uint8 [n, stride], length int16 [n], rate uint8 [n], status uint8 [n].
         Asynchronous on the handle's stream."""
         n = int(lts1_index.numel())
-        iq_samples = int(iq.numel() if iq.is_complex() else iq.numel() // 2)
+        iq_samples = self._dev_samples(iq)
         dbg = None
         if debug:
             dbg = Debug()
@@ -271,7 +289,7 @@ class Receiver:
     def sync_dev(self, iq, phase_in=0.0, tags=None, lts1_index=None, avail=None, phase=None):
         """iq: CUDA tensor float64 [2*n] / complex128 [n].  Optional outputs: tags uint8 [n], lts1_index int64
         [max_frames], avail int32 [max_frames], phase float64 [max_frames].  Returns the summary dict."""
-        n = int(iq.numel() if iq.is_complex() else iq.numel() // 2)
+        n = self._dev_samples(iq)
         res = SyncResult()
         rc = self.lib.b200rx_sync_dev(self.h, _ptr(iq), n, float(phase_in), _ptr(tags), _ptr(lts1_index), _ptr(avail),
                                       _ptr(phase), C.byref(res))
@@ -284,7 +302,7 @@ class Receiver:
         max_frames; slots beyond the frames found get status ST_NO_FRAME.  wait=True: returns the summary dict once
         the outputs are complete.  wait=False: asynchronous (pipelined over the lanes of set_pipeline_depth); the
         number of frames lands in the optional int32 [1] CUDA tensor `n_frames`."""
-        n = int(iq.numel() if iq.is_complex() else iq.numel() // 2)
+        n = self._dev_samples(iq)
         res = SyncResult()
         rc = self.lib.b200rx_receive_dev(self.h, _ptr(iq), n, float(phase_in), _ptr(payload),
                                          int(payload.shape[1]) if payload is not None else 0, _ptr(length), _ptr(rate),
@@ -297,8 +315,7 @@ class Receiver:
         """Host samples (complex128 array) -> (list of payload bytes of CRC-OK frames in stream order, info dict with
         per-frame status / length / rate / lts1 and the sync summary).  Mirrors receiver_chain::process_samples
         (receiver_chain.cpp:106-126) for one contiguous capture."""
-        iq = np.ascontiguousarray(samples, dtype=np.complex128)
-        n = int(iq.size)
+        iq, n = self._host_samples(samples)
         mf, stride = self.max_frames, max(1, self.max_payload_bytes)
         payload = np.zeros((mf, stride), dtype=np.uint8)
         length = np.zeros(mf, dtype=np.uint16)

@@ -106,6 +106,18 @@ B200RX_API const char *b200rx_version(void);
 B200RX_API int b200rx_set_stream(b200rx_handle *h, void *cuda_stream);
 B200RX_API int b200rx_synchronize(b200rx_handle *h);
 
+/* ---- sample format of every `iq` argument (wire-format ingestion) ----
+ * FC64 (default) is the reference's own std::complex<double> (tagged_vector.h:82-94; usrp.cpp:43 asks UHD for "fc64").
+ * FC32 and SC16 are what the same samples are on the radio side (usrp.cpp:44: wire format "sc16"): taking them as they
+ * are halves / quarters the bytes that cross PCIe, which is what bounds the host-buffer entry points.  Samples are
+ * widened to double in the kernels' loads - (double)float exactly, (double)int16 * sc16_scale with one rounding - and
+ * everything after that is the same fp64 arithmetic, so results are bit-identical to the reference fed the widened
+ * samples.  Applies to all later calls on the handle; `iq` pointers are then float[2] / int16_t[2] per sample. */
+#define B200RX_FMT_FC64 0
+#define B200RX_FMT_FC32 1
+#define B200RX_FMT_SC16 2
+B200RX_API int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale);
+
 #define B200RX_MAX_PIPELINE_DEPTH 6
 
 /* Pipelining of consecutive b200rx_decode_batch_dev calls.  depth = 1 (default): every call runs in order on
@@ -133,7 +145,9 @@ B200RX_API int b200rx_host_free(void *ptr);
  * returns when the results are in the caller's arrays.
  *
  *   iq            interleaved (re, im) doubles == std::complex<double>[] (the `sample` members of the
- *                 tagged_sample stream, tagged_vector.h:82-94); iq_samples complex samples in total
+ *                 tagged_sample stream, tagged_vector.h:82-94), or the format set by b200rx_set_sample_format;
+ *                 iq_samples complex samples in total.  If the buffer is pinned (b200rx_host_alloc, cudaHostRegister)
+ *                 the GPU reads it in place and fetches only the samples the path uses (no cyclic prefixes).
  *   lts1_index[f] index into iq of the sample timing_sync tagged LTS1 for frame f (timing_sync.cpp:105);
  *                 LTS2 is implied 64 samples later (timing_sync.cpp:106)
  *   avail[f]      complex samples available to frame f from lts1_index[f] on
@@ -142,14 +156,14 @@ B200RX_API int b200rx_host_free(void *ptr);
  *   rate_out      [n_frames] fun::Rate value or B200RX_RATE_INVALID
  *   status        [n_frames] B200RX_ST_*
  */
-B200RX_API int b200rx_decode_batch(b200rx_handle *h, const double *iq, uint64_t iq_samples,
+B200RX_API int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
                         const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
                         uint8_t *payload_out, uint32_t payload_stride,
                         uint16_t *payload_len, uint8_t *rate_out, uint8_t *status);
 
 /* Same contract with every array already in DEVICE memory; asynchronous on the handle's stream
  * (call b200rx_synchronize or sync the stream yourself).  dbg may be NULL. */
-B200RX_API int b200rx_decode_batch_dev(b200rx_handle *h, const double *iq_dev, uint64_t iq_samples,
+B200RX_API int b200rx_decode_batch_dev(b200rx_handle *h, const void *iq_dev, uint64_t iq_samples,
                             const uint64_t *lts1_index_dev, const uint32_t *avail_dev, uint32_t n_frames,
                             uint8_t *payload_out_dev, uint32_t payload_stride,
                             uint16_t *payload_len_dev, uint8_t *rate_out_dev, uint8_t *status_dev,
@@ -175,7 +189,7 @@ typedef struct b200rx_sync_result {
 /* Tags and frame list only.  tags_dev [n_samples] (nullable); lts1_index_dev / avail_dev [max_frames] as consumed by
  * b200rx_decode_batch_dev; phase_dev [max_frames] (nullable) the rotation phase of each frame.  phase_in is
  * m_phase_acc before the capture (0 for a fresh chain).  Synchronous: returns when `res` (host) is filled. */
-B200RX_API int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
+B200RX_API int b200rx_sync_dev(b200rx_handle *h, const void *iq_dev, uint64_t n_samples, double phase_in,
                                uint8_t *tags_dev, uint64_t *lts1_index_dev, uint32_t *avail_dev, double *phase_dev,
                                b200rx_sync_result *res);
 
@@ -185,13 +199,13 @@ B200RX_API int b200rx_sync_dev(b200rx_handle *h, const double *iq_dev, uint64_t 
  * in stream order, the rest get status B200RX_ST_NO_FRAME.  lts1_out_dev [max_frames] and n_frames_dev [1] are
  * optional.  res != NULL: the call returns when the summary is on the host (outputs complete).  res == NULL: fully
  * asynchronous, pipelined over the lanes of b200rx_set_pipeline_depth like b200rx_decode_batch_dev. */
-B200RX_API int b200rx_receive_dev(b200rx_handle *h, const double *iq_dev, uint64_t n_samples, double phase_in,
+B200RX_API int b200rx_receive_dev(b200rx_handle *h, const void *iq_dev, uint64_t n_samples, double phase_in,
                                   uint8_t *payload_out_dev, uint32_t payload_stride, uint16_t *payload_len_dev,
                                   uint8_t *rate_out_dev, uint8_t *status_dev, uint64_t *lts1_out_dev,
                                   uint32_t *n_frames_dev, b200rx_sync_result *res);
 
 /* Same with host buffers (pinned buffers recommended); synchronous. */
-B200RX_API int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_samples, double phase_in,
+B200RX_API int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n_samples, double phase_in,
                               uint8_t *payload_out, uint32_t payload_stride, uint16_t *payload_len, uint8_t *rate_out,
                               uint8_t *status, uint64_t *lts1_out, b200rx_sync_result *res);
 
@@ -199,7 +213,7 @@ B200RX_API int b200rx_receive(b200rx_handle *h, const double *iq, uint64_t n_sam
  * SIGNAL symbol are read (208 samples from lts1_index[f]); gives the streaming adapter the frame length
  * before the frame has fully arrived.  HOST buffers, synchronous.  status: B200RX_ST_OK (header valid; the
  * frame needs 128 + 80 * (1 + nsym) samples), HDR_PARITY, HDR_RATE, TOO_LONG, or TRUNCATED (< 208 samples). */
-B200RX_API int b200rx_decode_headers(b200rx_handle *h, const double *iq, uint64_t iq_samples,
+B200RX_API int b200rx_decode_headers(b200rx_handle *h, const void *iq, uint64_t iq_samples,
                                      const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
                                      uint16_t *payload_len, uint8_t *rate_out, uint8_t *status);
 

@@ -1,0 +1,152 @@
+"""GPU parity of the wire-format ingestion: fc32 / sc16 samples through the C ABI against the
+checker fed the same samples widened to std::complex<double> on the host.  Widening is exact for fc32 and one
+IEEE multiply for sc16, so every integer output is BIT-EXACT and the constellation is within 1e-9.
+
+Also covers the pinned-buffer ingest of the host entry point (ingest.cu: the GPU pulls only the samples the
+path uses): it must give what the device-resident path gives, for every format.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ofdm_testutil import checker_decode, make_corpus
+from test_gpu_parity import compare
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def narrow(iq, fmt):
+    """complex128 samples -> (array in the wire format, sc16 scale, the same samples widened back to complex128)"""
+    import fun_ofdm_b200 as fo
+    if fmt == fo.FMT_FC64:
+        return iq, 1.0, iq
+    if fmt == fo.FMT_FC32:
+        w = iq.astype(np.complex64)
+        return w, 1.0, w.astype(np.complex128)
+    scale = float(np.max(np.abs(iq.view(np.float64)))) / 30000.0  # leave head room like an ADC would
+    q = np.clip(np.rint(iq.view(np.float64) / scale), -32768, 32767).astype(np.int16)
+    wide = (q.astype(np.float64) * scale).view(np.complex128)
+    return q, scale, wide
+
+
+def dev_decode(rx, wire, corpus, taps=True):
+    dev = torch.device("cuda:0")
+    n = len(corpus["lts1"])
+    raw = np.ascontiguousarray(wire)
+    iq = torch.from_numpy(raw.view(np.uint8)).to(dev)
+    lts1 = torch.from_numpy(corpus["lts1"]).to(dev)
+    avail = torch.from_numpy(corpus["avail"]).to(dev)
+    payload = torch.zeros((n, rx.max_payload_bytes), dtype=torch.uint8, device=dev)
+    length = torch.zeros(n, dtype=torch.int16, device=dev)
+    rate = torch.zeros(n, dtype=torch.uint8, device=dev)
+    status = torch.full((n,), 99, dtype=torch.uint8, device=dev)
+    dbg = None
+    if taps:
+        max_vec = int(max((a - 128) // 80 for a in corpus["avail"])) + 1
+        dbg = dict(equalized=torch.zeros((n, max_vec, 48, 2), dtype=torch.float64, device=dev),
+                   decoded=torch.zeros((n, rx.max_steps // 8 + 8), dtype=torch.uint8, device=dev),
+                   header_field=torch.zeros(n, dtype=torch.int32, device=dev),
+                   depunct=torch.zeros((n, 2 * rx.max_steps), dtype=torch.uint8, device=dev))
+    rx.decode_batch_dev(iq, lts1, avail, payload, length, rate, status, dbg)
+    rx.synchronize()
+    out = dict(payload=payload.cpu().numpy(), length=length.cpu().numpy().astype(np.uint16).astype(int),
+               rate=rate.cpu().numpy(), status=status.cpu().numpy())
+    if taps:
+        out.update({k: v.cpu().numpy() for k, v in dbg.items()})
+    return out
+
+
+@pytest.mark.parametrize("fmt_name", ["fc32", "sc16"])
+def test_wire_formats_bit_exact(ref, rx_factory, fmt_name):
+    import fun_ofdm_b200 as fo
+    fmt = {"fc32": fo.FMT_FC32, "sc16": fo.FMT_SC16}[fmt_name]
+    rng = np.random.default_rng(404 + fmt)
+    rx = rx_factory(64, 1500)
+    total = 0
+    try:
+        # no noiseless case here: quantised noiseless BPSK puts equalised points within 1 ulp of -1, exactly on the
+        # demapper's truncation boundary (qam.h:112), where the last bit of any two FFT implementations decides
+        # (also true of the reference's FFTW vs the checker's shim; SURVEY 8c "parity unpinned at bit level")
+        for snr in (40, 26, 17):
+            rates = list(range(11)) + [10, 10, 8]
+            lengths = [1500] + list(rng.integers(0, 1500, len(rates) - 1))
+            corpus = make_corpus(ref, rng, rates, lengths, snr_db=snr)
+            wire, scale, wide = narrow(corpus["iq"], fmt)
+            rx.set_sample_format(fmt, scale)
+            ref_corpus = dict(corpus, iq=wide)
+            want = checker_decode(ref, ref_corpus)
+            got = dev_decode(rx, wire, corpus)
+            total += compare(corpus, got, want)
+    finally:
+        rx.set_sample_format(fo.FMT_FC64)
+    assert total > 10
+
+
+@pytest.mark.parametrize("fmt_name", ["fc64", "fc32", "sc16"])
+def test_pinned_host_ingest_matches_device_path(ref, rx_factory, fmt_name):
+    """b200rx_decode_batch on a pinned buffer (GPU pulls the useful samples over PCIe) == pageable buffer (DMA copy)
+    == device-resident path, frame by frame; odd frame offsets exercise unaligned sample addresses."""
+    import fun_ofdm_b200 as fo
+    fmt = {"fc64": fo.FMT_FC64, "fc32": fo.FMT_FC32, "sc16": fo.FMT_SC16}[fmt_name]
+    rng = np.random.default_rng(505 + fmt)
+    n = 300  # > 2 * the smallest chunk: takes the chunked pipeline
+    rx = rx_factory(512, 1500)
+    rates = list(rng.integers(0, 11, n))
+    lengths = list(rng.integers(0, 400, n))
+    lengths[0] = 1500
+    corpus = make_corpus(ref, rng, rates, lengths, snr_db=24, gap=61)
+    corpus["avail"][5] = 150
+    corpus["avail"][9] -= 100
+    wire, scale, wide = narrow(corpus["iq"], fmt)
+    lib = fo.load_library()
+    try:
+        rx.set_sample_format(fmt, scale)
+        want = dev_decode(rx, wire, corpus, taps=False)
+        pageable = rx.decode_batch(wire, corpus["lts1"], corpus["avail"])
+        raw = np.ascontiguousarray(wire).view(np.uint8).reshape(-1)
+        p = C.c_void_p()
+        assert lib.b200rx_host_alloc(C.byref(p), raw.nbytes) == 0
+        try:
+            C.memmove(p, raw.ctypes.data, raw.nbytes)
+            pinned_view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(raw.nbytes,)).view(wire.dtype)
+            launches0 = rx.launch_count
+            pinned = rx.decode_batch(pinned_view, corpus["lts1"], corpus["avail"])
+            assert rx.launch_count - launches0 > 3, "pinned buffers must take the pull path"
+        finally:
+            lib.b200rx_host_free(p)
+    finally:
+        rx.set_sample_format(fo.FMT_FC64)
+    for name, got in (("pageable", pageable), ("pinned", pinned)):
+        payload, length, rate, status = got
+        assert np.array_equal(status, want["status"]), name
+        assert np.array_equal(rate, want["rate"]), name
+        assert np.array_equal(length.astype(int), want["length"]), name
+        for f in range(n):
+            assert bytes(payload[f, : length[f]]) == bytes(want["payload"][f, : length[f]]), (name, f)
+    # and the device path itself agrees with the checker on the widened samples
+    chk = checker_decode(ref, dict(corpus, iq=wide))
+    assert compare(corpus, want, chk, taps=False) > n // 2
+
+
+def test_receive_from_sc16_capture(ref, rx_factory):
+    """Raw sc16 capture -> detector + sync + decode; same frames and payloads as the fc64 path on the widened samples."""
+    import fun_ofdm_b200 as fo
+    rng = np.random.default_rng(606)
+    rx = rx_factory(64, 1500)
+    rates = [10, 8, 5, 3, 0, 10, 9, 6]
+    lengths = [300, 200, 100, 150, 40, 500, 333, 64]
+    corpus = make_corpus(ref, rng, rates, lengths, snr_db=27, gap=400)
+    iq = np.concatenate([corpus["iq"], np.zeros(400, complex)])
+    wire, scale, wide = narrow(iq, fo.FMT_SC16)
+    out_wide, info_wide = rx.receive(wide)
+    try:
+        rx.set_sample_format(fo.FMT_SC16, scale)
+        out_q, info_q = rx.receive(wire)
+    finally:
+        rx.set_sample_format(fo.FMT_FC64)
+    assert np.array_equal(info_q["lts1"], info_wide["lts1"])
+    assert np.array_equal(info_q["status"], info_wide["status"])
+    assert out_q == out_wide
+    assert len(out_q) >= 6
