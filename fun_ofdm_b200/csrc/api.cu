@@ -34,14 +34,24 @@ struct b200rx_handle {
     uint32_t *dec = nullptr; // survivor words: 2 per trellis step per frame
     unsigned long long *counters = nullptr; // 8 words (5 used)
 
-    // staging for the host-buffer entry point (grow-only)
-    uint8_t *d_iq = nullptr; size_t d_iq_cap = 0; // bytes, samples in the handle's format
-    uint64_t *d_lts1 = nullptr;
-    uint32_t *d_avail = nullptr;
-    uint8_t *d_payload = nullptr; size_t d_payload_cap = 0;
-    uint16_t *d_len = nullptr;
-    uint8_t *d_rate = nullptr;
-    uint8_t *d_status = nullptr;
+    // staging of the host-buffer entry points (grow-only).  b200rx_submit_batch keeps up to B200RX_MAX_INFLIGHT calls in
+    // flight, each on its own slot: staging + decode scratch + completion event.  Slot 0's scratch is lane 0's.
+    struct HostSlot {
+        uint8_t *d_iq = nullptr; size_t d_iq_cap = 0; // bytes, samples in the handle's format
+        uint64_t *d_lts1 = nullptr;
+        uint32_t *d_avail = nullptr;
+        uint8_t *d_payload = nullptr; size_t d_payload_cap = 0;
+        uint16_t *d_len = nullptr;
+        uint8_t *d_rate = nullptr;
+        uint8_t *d_status = nullptr;
+        FrameDesc *desc = nullptr; uint32_t *bm = nullptr; uint32_t *dec = nullptr; unsigned long long *counters = nullptr;
+        std::vector<cudaEvent_t> pipe_ev; // 2 per chunk (samples landed, results ready) + 1
+        cudaEvent_t done = nullptr;
+        bool busy = false;
+        uint64_t ticket = 0;
+    };
+    HostSlot hs[B200RX_MAX_INFLIGHT];
+    uint64_t next_ticket = 1;
 
     // pipeline depth > 1: consecutive device-buffer calls rotate over `depth` lanes (own scratch set, own stream),
     // so that batch j+1 starts while batch j is still in its Viterbi kernel (b200rx_set_pipeline_depth)
@@ -55,8 +65,7 @@ struct b200rx_handle {
     cudaEvent_t ev_in = nullptr;
 
     // host-buffer pipeline: H2D of chunk i+1 overlaps the kernels of chunk i
-    cudaStream_t copy_stream = nullptr, aux_stream[3] = {nullptr, nullptr, nullptr}, d2h_stream = nullptr;
-    std::vector<cudaEvent_t> pipe_ev; // 2 per chunk: samples landed, results ready
+    cudaStream_t copy_stream = nullptr, pull_stream = nullptr, aux_stream[7] = {}, d2h_stream = nullptr;
 
     // frame detection / timing synchronisation scratch, one set per pipeline lane (allocated on first use)
     struct SyncScratch {
@@ -112,6 +121,18 @@ inline void use_lane(b200rx_handle *h, int i)
         cudaError_t ce_ = (call);                                           \
         if (ce_ != cudaSuccess) return fail(h, B200RX_E_CUDA, #call, ce_);  \
     } while (0)
+
+// Host-buffer calls still in flight (b200rx_submit_batch) own scratch the other entry points use: finish them first.
+inline int quiesce_host(b200rx_handle *h)
+{
+    for (auto &S : h->hs)
+        if (S.busy) {
+            CU(h, cudaEventSynchronize(S.done));
+            S.busy = false;
+        }
+    if (h->depth <= 1) use_lane(h, 0);
+    return B200RX_OK;
+}
 
 // ---- constant tables (regenerated from their defining rules; pinned by tests against the reference) ----
 bool g_tables_uploaded[64] = {false};
@@ -237,7 +258,8 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 3; i++)
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->pull_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 7; i++)
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
@@ -245,11 +267,11 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     A((void **)&h->bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
     A((void **)&h->dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
     A((void **)&h->counters, 8 * sizeof(unsigned long long));
-    A((void **)&h->d_lts1, nf * sizeof(uint64_t));
-    A((void **)&h->d_avail, nf * sizeof(uint32_t));
-    A((void **)&h->d_len, nf * sizeof(uint16_t));
-    A((void **)&h->d_rate, nf);
-    A((void **)&h->d_status, nf);
+    A((void **)&h->hs[0].d_lts1, nf * sizeof(uint64_t));
+    A((void **)&h->hs[0].d_avail, nf * sizeof(uint32_t));
+    A((void **)&h->hs[0].d_len, nf * sizeof(uint16_t));
+    A((void **)&h->hs[0].d_rate, nf);
+    A((void **)&h->hs[0].d_status, nf);
     if (e != cudaSuccess) {
         int code = (e == cudaErrorMemoryAllocation) ? B200RX_E_NOMEM : B200RX_E_CUDA;
         fail(nullptr, code, "b200rx_create: allocating device scratch", e);
@@ -258,6 +280,7 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     }
     h->stream = h->own_stream;
     h->lanes[0].desc = h->desc; h->lanes[0].bm = h->bm; h->lanes[0].dec = h->dec; h->lanes[0].counters = h->counters;
+    h->hs[0].desc = h->desc; h->hs[0].bm = h->bm; h->hs[0].dec = h->dec; h->hs[0].counters = h->counters;
     *out = h;
     return B200RX_OK;
 }
@@ -281,13 +304,19 @@ int b200rx_destroy(b200rx_handle *h)
     if (h->sy_summary_host) cudaFreeHost(h->sy_summary_host);
     use_lane(h, 0);
     cudaFree(h->desc); cudaFree(h->bm); cudaFree(h->dec); cudaFree(h->counters);
-    cudaFree(h->d_iq); cudaFree(h->d_lts1); cudaFree(h->d_avail); cudaFree(h->d_payload);
-    cudaFree(h->d_len); cudaFree(h->d_rate); cudaFree(h->d_status);
+    for (int i = 0; i < B200RX_MAX_INFLIGHT; i++) {
+        b200rx_handle::HostSlot &S = h->hs[i];
+        if (S.done) { cudaEventSynchronize(S.done); cudaEventDestroy(S.done); }
+        cudaFree(S.d_iq); cudaFree(S.d_lts1); cudaFree(S.d_avail); cudaFree(S.d_payload);
+        cudaFree(S.d_len); cudaFree(S.d_rate); cudaFree(S.d_status);
+        if (i > 0) { cudaFree(S.desc); cudaFree(S.bm); cudaFree(S.dec); cudaFree(S.counters); }
+        for (cudaEvent_t e : S.pipe_ev) if (e) cudaEventDestroy(e);
+    }
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
-    for (cudaEvent_t e : h->pipe_ev) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    for (int i = 0; i < 3; i++)
+    if (h->pull_stream) cudaStreamDestroy(h->pull_stream);
+    for (int i = 0; i < 7; i++)
         if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -319,6 +348,11 @@ int b200rx_synchronize(b200rx_handle *h)
     CU(h, cudaSetDevice(h->device));
     for (int i = 0; i < B200RX_MAX_PIPELINE_DEPTH; i++)
         if (h->lanes[i].stream && h->lanes[i].used) CU(h, cudaStreamSynchronize(h->lanes[i].stream));
+    for (auto &S : h->hs)
+        if (S.busy) {
+            CU(h, cudaEventSynchronize(S.done));
+            S.busy = false;
+        }
     CU(h, cudaStreamSynchronize(h->stream));
     return B200RX_OK;
 }
@@ -470,6 +504,7 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const void *iq_dev, uint64_t iq_sa
     if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_batch_dev: n_frames exceeds max_frames");
     if (n_frames == 0) return B200RX_OK;
     CU(h, cudaSetDevice(h->device));
+    { int rcq = quiesce_host(h); if (rcq != B200RX_OK) return rcq; }
     cudaStream_t s = h->stream;
     b200rx_handle::Lane *lane = nullptr;
     if (h->depth > 1) {
@@ -494,63 +529,136 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const void *iq_dev, uint64_t iq_sa
     return B200RX_OK;
 }
 
+namespace {
+
+// scratch + small staging arrays of host slot k (slot 0 got them in b200rx_create)
+int ensure_host_slot(b200rx_handle *h, int k)
+{
+    b200rx_handle::HostSlot &S = h->hs[k];
+    if (!S.done) CU(h, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    if (S.desc) return B200RX_OK;
+    const size_t nf = h->limits.max_frames;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void **)&S.desc, nf * sizeof(FrameDesc));
+    A((void **)&S.bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
+    A((void **)&S.dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
+    A((void **)&S.counters, 8 * sizeof(unsigned long long));
+    A((void **)&S.d_lts1, nf * sizeof(uint64_t));
+    A((void **)&S.d_avail, nf * sizeof(uint32_t));
+    A((void **)&S.d_len, nf * sizeof(uint16_t));
+    A((void **)&S.d_rate, nf);
+    A((void **)&S.d_status, nf);
+    if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_submit_batch: scratch for another call in flight", e);
+    return B200RX_OK;
+}
+
+int wait_slot(b200rx_handle *h, b200rx_handle::HostSlot &S)
+{
+    if (S.busy) {
+        CU(h, cudaEventSynchronize(S.done));
+        S.busy = false;
+    }
+    return B200RX_OK;
+}
+
+} // namespace
+
+int b200rx_wait(b200rx_handle *h, uint64_t ticket)
+{
+    if (!h) return B200RX_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    for (auto &S : h->hs)
+        if (S.busy && (ticket == 0 || S.ticket == ticket)) {
+            int rc = wait_slot(h, S);
+            if (rc != B200RX_OK) return rc;
+        }
+    return B200RX_OK;
+}
+
 int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
                         const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
                         uint8_t *payload_out, uint32_t payload_stride,
                         uint16_t *payload_len, uint8_t *rate_out, uint8_t *status)
 {
+    uint64_t ticket = 0;
+    int rc = b200rx_submit_batch(h, iq, iq_samples, lts1_index, avail, n_frames, payload_out, payload_stride, payload_len,
+                                 rate_out, status, &ticket);
+    if (rc != B200RX_OK) return rc;
+    return b200rx_wait(h, ticket);
+}
+
+int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
+                        const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
+                        uint8_t *payload_out, uint32_t payload_stride,
+                        uint16_t *payload_len, uint8_t *rate_out, uint8_t *status, uint64_t *ticket)
+{
     if (!h) return B200RX_E_ARG;
-    if (!iq || !lts1_index || !avail || !status) return fail(h, B200RX_E_ARG, "b200rx_decode_batch: null argument");
-    if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_batch: n_frames exceeds max_frames");
+    if (!iq || !lts1_index || !avail || !status || !ticket) return fail(h, B200RX_E_ARG, "b200rx_submit_batch: null argument");
+    if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_submit_batch: n_frames exceeds max_frames");
+    *ticket = 0;
     if (n_frames == 0) return B200RX_OK;
-    if (h->depth > 1) { // these entry points are not pipelined: drain the lanes, work on scratch set 0
-        int rcq = b200rx_synchronize(h);
-        if (rcq != B200RX_OK) return rcq;
-        use_lane(h, 0);
-    }
     CU(h, cudaSetDevice(h->device));
+    if (h->depth > 1) { // the device-buffer lanes share scratch set 0 with host slot 0: drain them
+        for (int i = 0; i < B200RX_MAX_PIPELINE_DEPTH; i++)
+            if (h->lanes[i].stream && h->lanes[i].used) CU(h, cudaStreamSynchronize(h->lanes[i].stream));
+    }
+    // slot: round robin; a slot still in flight is waited for (at most B200RX_MAX_INFLIGHT calls overlap)
+    const int k = (int)(h->next_ticket % B200RX_MAX_INFLIGHT);
+    b200rx_handle::HostSlot &S = h->hs[k];
+    { int rcw = wait_slot(h, S); if (rcw != B200RX_OK) return rcw; }
+    { int rce = ensure_host_slot(h, k); if (rce != B200RX_OK) return rce; }
     cudaStream_t s = h->stream;
+    h->desc = S.desc; h->bm = S.bm; h->dec = S.dec; h->counters = S.counters;
 
     const size_t bps = sample_bytes(h->fmt);
     const size_t iq_bytes = (size_t)iq_samples * bps;
-    if (iq_bytes > h->d_iq_cap) {
-        if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
-        cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
-        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_decode_batch: sample staging", e);
-        h->d_iq_cap = iq_bytes;
+    if (iq_bytes > S.d_iq_cap) {
+        if (S.d_iq) { cudaFree(S.d_iq); S.d_iq = nullptr; S.d_iq_cap = 0; } // the slot is idle: nothing reads it
+        cudaError_t e = cudaMalloc((void **)&S.d_iq, iq_bytes);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_submit_batch: sample staging", e);
+        S.d_iq_cap = iq_bytes;
     }
     const size_t pl_bytes = payload_out ? (size_t)n_frames * payload_stride : 0;
-    if (pl_bytes > h->d_payload_cap) {
-        if (h->d_payload) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_payload); h->d_payload = nullptr; h->d_payload_cap = 0; }
-        cudaError_t e = cudaMalloc((void **)&h->d_payload, pl_bytes);
-        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_decode_batch: payload staging", e);
-        h->d_payload_cap = pl_bytes;
+    if (pl_bytes > S.d_payload_cap) {
+        if (S.d_payload) { cudaFree(S.d_payload); S.d_payload = nullptr; S.d_payload_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&S.d_payload, pl_bytes);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_submit_batch: payload staging", e);
+        S.d_payload_cap = pl_bytes;
     }
-    CU(h, cudaMemcpyAsync(h->d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
-    const OutPtrs o{payload_out ? h->d_payload : nullptr, payload_stride, h->d_len, h->d_rate, h->d_status};
+    CU(h, cudaMemcpyAsync(S.d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(S.d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long), s));
+    const OutPtrs o{payload_out ? S.d_payload : nullptr, payload_stride, S.d_len, S.d_rate, S.d_status};
+    auto finish = [&](cudaStream_t last) -> int {
+        CU(h, cudaEventRecord(S.done, last));
+        S.busy = true;
+        S.ticket = h->next_ticket++;
+        *ticket = S.ticket;
+        return B200RX_OK;
+    };
 
     // Chunked pipeline: the samples of chunk i+1 cross PCIe while chunk i is decoded (kernels of consecutive
     // chunks rotate over four streams so that their Viterbi kernels overlap) and chunk i-1's results go
     // back.  Needs the frames in stream order (lts1_index non-decreasing); otherwise one copy, one batch.
-    // The copy is the bottleneck, so what matters is how long the decode of the LAST chunk takes after its
-    // samples have landed: chunks start at CH frames and halve towards the end of the batch (down to CH_MIN).
-    static const uint32_t CH = [] { // tuning knobs for experiments
+    // The copy is the bottleneck, so what matters for one call on its own is how long the decode of the LAST chunk
+    // takes after its samples have landed: chunks start at CH frames and halve towards the end (down to CH_MIN).
+    const uint32_t CH = [] { // tuning knobs for experiments
         const char *e = getenv("B200RX_H2D_CHUNK");
         long v = e ? atol(e) : 0;
         return (uint32_t)(v >= 32 ? v : 1024);
     }();
-    static const uint32_t CH_MIN = [] {
+    const uint32_t CH_MIN = [] {
         const char *e = getenv("B200RX_H2D_CHUNK_MIN");
         long v = e ? atol(e) : 0;
-        return (uint32_t)(v >= 16 ? v : 64);
+        return (uint32_t)(v >= 16 ? v : 256);
     }();
-    // Pinned caller buffer: the GPU pulls the useful samples itself (ingest.cu) instead of a DMA copy of everything.
-    const char *pull_env = getenv("B200RX_PULL"); // B200RX_PULL=0: always DMA-copy (for A/B measurements)
-    const bool PULL = !(pull_env && atoi(pull_env) == 0);
+    // Pinned caller buffer: the GPU can pull the useful samples itself (ingest.cu) instead of a DMA copy of everything.
+    const char *pull_env = getenv("B200RX_PULL"); // 0: always DMA-copy, 1: pull whenever the buffer is pinned, 2: alternate
+    const int pull_mode = pull_env ? atoi(pull_env) : (h->fmt == FMT_FC64 ? 1 : 0); // narrow formats: the DMA engine wins
+    const bool pull_wanted = pull_mode != 0;
     const void *iq_mapped = nullptr;
-    if (PULL) {
+    if (pull_wanted) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, iq) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             iq_mapped = at.devicePointer;
@@ -560,15 +668,14 @@ int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     bool ordered = n_frames > 2 * CH_MIN;
     for (uint32_t f = 1; ordered && f < n_frames; f++) ordered = lts1_index[f] >= lts1_index[f - 1];
     if (!ordered) {
-        CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
-        int rc = launch_range(h, s, 0, n_frames, h->d_iq, iq_samples, h->d_lts1, h->d_avail, o, nullptr, nullptr);
+        CU(h, cudaMemcpyAsync(S.d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+        int rc = launch_range(h, s, 0, n_frames, S.d_iq, iq_samples, S.d_lts1, S.d_avail, o, nullptr, nullptr);
         if (rc != B200RX_OK) return rc;
-        if (payload_out) CU(h, cudaMemcpyAsync(payload_out, h->d_payload, pl_bytes, cudaMemcpyDeviceToHost, s));
-        if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
-        if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, n_frames, cudaMemcpyDeviceToHost, s));
-        CU(h, cudaMemcpyAsync(status, h->d_status, n_frames, cudaMemcpyDeviceToHost, s));
-        CU(h, cudaStreamSynchronize(s));
-        return B200RX_OK;
+        if (payload_out) CU(h, cudaMemcpyAsync(payload_out, S.d_payload, pl_bytes, cudaMemcpyDeviceToHost, s));
+        if (payload_len) CU(h, cudaMemcpyAsync(payload_len, S.d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+        if (rate_out) CU(h, cudaMemcpyAsync(rate_out, S.d_rate, n_frames, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(status, S.d_status, n_frames, cudaMemcpyDeviceToHost, s));
+        return finish(s);
     }
     std::vector<uint32_t> bound(1, 0u); // chunk c = frames [bound[c], bound[c+1])
     for (uint32_t f = 0; f < n_frames;) {
@@ -579,15 +686,16 @@ int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
         bound.push_back(f);
     }
     const uint32_t n_chunks = (uint32_t)bound.size() - 1;
-    while (h->pipe_ev.size() < 2 * (size_t)n_chunks + 1) {
+    while (S.pipe_ev.size() < 2 * (size_t)n_chunks + 1) {
         cudaEvent_t e;
         CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        h->pipe_ev.push_back(e);
+        S.pipe_ev.push_back(e);
     }
-    cudaEvent_t ev_start = h->pipe_ev[2 * n_chunks];
-    CU(h, cudaEventRecord(ev_start, s)); // staging buffers (re)allocated, small arrays and counter reset queued
+    cudaEvent_t ev_start = S.pipe_ev[2 * n_chunks];
+    CU(h, cudaEventRecord(ev_start, s)); // small arrays and counter reset queued
     CU(h, cudaStreamWaitEvent(h->copy_stream, ev_start, 0));
-    for (int i = 0; i < 3; i++) CU(h, cudaStreamWaitEvent(h->aux_stream[i], ev_start, 0));
+    CU(h, cudaStreamWaitEvent(h->pull_stream, ev_start, 0));
+    for (int i = 0; i < 7; i++) CU(h, cudaStreamWaitEvent(h->aux_stream[i], ev_start, 0));
     uint64_t copied = 0; // samples [0, copied) are on their way
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t f0 = bound[c], f1 = bound[c + 1];
@@ -599,35 +707,35 @@ int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
         }
         uint64_t lo = lts1_index[f0] < iq_samples ? lts1_index[f0] : iq_samples;
         if (lo < copied) lo = copied;
-        if (iq_mapped) {
-            CU(h, launch_pull(iq_mapped, h->d_iq, h->fmt, iq_samples, h->d_lts1 + f0, h->d_avail + f0, f1 - f0, h->sm_count,
-                              h->copy_stream));
+        const bool pull_this = iq_mapped && (pull_mode != 2 || (c & 1)); // mode 2: the DMA engine and the SMs share the link
+        cudaStream_t in_stream = pull_this ? h->pull_stream : h->copy_stream;
+        if (pull_this) {
+            CU(h, launch_pull(iq_mapped, S.d_iq, h->fmt, iq_samples, S.d_lts1 + f0, S.d_avail + f0, f1 - f0, h->sm_count,
+                              in_stream));
             h->launches++;
         } else if (hi > lo) {
-            CU(h, cudaMemcpyAsync(h->d_iq + lo * bps, (const uint8_t *)iq + lo * bps, (size_t)(hi - lo) * bps,
-                                  cudaMemcpyHostToDevice, h->copy_stream));
-            copied = hi;
+            CU(h, cudaMemcpyAsync(S.d_iq + lo * bps, (const uint8_t *)iq + lo * bps, (size_t)(hi - lo) * bps,
+                                  cudaMemcpyHostToDevice, in_stream));
+            if (pull_mode != 2) copied = hi;
         }
-        cudaEvent_t ev_in = h->pipe_ev[2 * c], ev_out = h->pipe_ev[2 * c + 1];
-        CU(h, cudaEventRecord(ev_in, h->copy_stream));
-        cudaStream_t cs = (c & 3) ? h->aux_stream[(c & 3) - 1] : s;
+        cudaEvent_t ev_in = S.pipe_ev[2 * c], ev_out = S.pipe_ev[2 * c + 1];
+        CU(h, cudaEventRecord(ev_in, in_stream));
+        cudaStream_t cs = (c & 7) ? h->aux_stream[(c & 7) - 1] : s;
         CU(h, cudaStreamWaitEvent(cs, ev_in, 0));
-        int rc = launch_range(h, cs, f0, f1 - f0, h->d_iq, iq_samples, h->d_lts1, h->d_avail, o, nullptr, nullptr);
+        int rc = launch_range(h, cs, f0, f1 - f0, S.d_iq, iq_samples, S.d_lts1, S.d_avail, o, nullptr, nullptr);
         if (rc != B200RX_OK) return rc;
         CU(h, cudaEventRecord(ev_out, cs));
         CU(h, cudaStreamWaitEvent(h->d2h_stream, ev_out, 0));
         const uint32_t nf = f1 - f0;
         if (payload_out)
-            CU(h, cudaMemcpyAsync(payload_out + (size_t)f0 * payload_stride, h->d_payload + (size_t)f0 * payload_stride,
+            CU(h, cudaMemcpyAsync(payload_out + (size_t)f0 * payload_stride, S.d_payload + (size_t)f0 * payload_stride,
                                   (size_t)nf * payload_stride, cudaMemcpyDeviceToHost, h->d2h_stream));
-        if (payload_len) CU(h, cudaMemcpyAsync(payload_len + f0, h->d_len + f0, nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->d2h_stream));
-        if (rate_out) CU(h, cudaMemcpyAsync(rate_out + f0, h->d_rate + f0, nf, cudaMemcpyDeviceToHost, h->d2h_stream));
-        CU(h, cudaMemcpyAsync(status + f0, h->d_status + f0, nf, cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (payload_len) CU(h, cudaMemcpyAsync(payload_len + f0, S.d_len + f0, nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (rate_out) CU(h, cudaMemcpyAsync(rate_out + f0, S.d_rate + f0, nf, cudaMemcpyDeviceToHost, h->d2h_stream));
+        CU(h, cudaMemcpyAsync(status + f0, S.d_status + f0, nf, cudaMemcpyDeviceToHost, h->d2h_stream));
     }
-    CU(h, cudaStreamSynchronize(h->d2h_stream));
-    for (int i = 0; i < 3; i++) CU(h, cudaStreamSynchronize(h->aux_stream[i]));
-    CU(h, cudaStreamSynchronize(s));
-    return B200RX_OK;
+    // every chunk's kernels are ordered before its copies on d2h_stream, so its tail is the end of the call
+    return finish(h->d2h_stream);
 }
 
 namespace {
@@ -691,6 +799,7 @@ int fetch_summary(b200rx_handle *h, cudaStream_t s, int lane, double phase_in, b
 
 int drain_lanes(b200rx_handle *h)
 {
+    { int rcq = quiesce_host(h); if (rcq != B200RX_OK) return rcq; }
     if (h->depth > 1) { // not pipelined: drain the lanes, work on scratch set 0
         int rcq = b200rx_synchronize(h);
         if (rcq != B200RX_OK) return rcq;
@@ -732,6 +841,7 @@ int b200rx_receive_dev(b200rx_handle *h, const void *iq_dev, uint64_t n_samples,
     if (!h) return B200RX_E_ARG;
     if ((!iq_dev && n_samples) || !status_dev) return fail(h, B200RX_E_ARG, "b200rx_receive_dev: null argument");
     CU(h, cudaSetDevice(h->device));
+    { int rcq = quiesce_host(h); if (rcq != B200RX_OK) return rcq; }
     cudaStream_t s = h->stream;
     b200rx_handle::Lane *lane = nullptr;
     int li = 0;
@@ -775,30 +885,30 @@ int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n_samples, double 
     if (rc != B200RX_OK) return rc;
     cudaStream_t s = h->stream;
     const size_t iq_bytes = (size_t)n_samples * sample_bytes(h->fmt);
-    if (iq_bytes > h->d_iq_cap) {
-        if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
-        cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
+    if (iq_bytes > h->hs[0].d_iq_cap) {
+        if (h->hs[0].d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->hs[0].d_iq); h->hs[0].d_iq = nullptr; h->hs[0].d_iq_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->hs[0].d_iq, iq_bytes);
         if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_receive: sample staging", e);
-        h->d_iq_cap = iq_bytes;
+        h->hs[0].d_iq_cap = iq_bytes;
     }
     const size_t pl_cap = payload_out ? (size_t)h->limits.max_frames * payload_stride : 0;
-    if (pl_cap > h->d_payload_cap) {
-        if (h->d_payload) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_payload); h->d_payload = nullptr; h->d_payload_cap = 0; }
-        cudaError_t e = cudaMalloc((void **)&h->d_payload, pl_cap);
+    if (pl_cap > h->hs[0].d_payload_cap) {
+        if (h->hs[0].d_payload) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->hs[0].d_payload); h->hs[0].d_payload = nullptr; h->hs[0].d_payload_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->hs[0].d_payload, pl_cap);
         if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_receive: payload staging", e);
-        h->d_payload_cap = pl_cap;
+        h->hs[0].d_payload_cap = pl_cap;
     }
-    if (iq_bytes) CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    if (iq_bytes) CU(h, cudaMemcpyAsync(h->hs[0].d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
     const int li = h->depth > 1 ? (int)(h->call_idx % h->depth) : 0; // scratch set the next call uses
-    rc = b200rx_receive_dev(h, h->d_iq, n_samples, phase_in, payload_out ? h->d_payload : nullptr, payload_stride, h->d_len,
-                            h->d_rate, h->d_status, nullptr, nullptr, res);
+    rc = b200rx_receive_dev(h, h->hs[0].d_iq, n_samples, phase_in, payload_out ? h->hs[0].d_payload : nullptr, payload_stride, h->hs[0].d_len,
+                            h->hs[0].d_rate, h->hs[0].d_status, nullptr, nullptr, res);
     if (rc != B200RX_OK) return rc;
     const size_t nf = res->n_frames;
     if (nf) {
-        if (payload_out) CU(h, cudaMemcpyAsync(payload_out, h->d_payload, nf * payload_stride, cudaMemcpyDeviceToHost, s));
-        if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
-        if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, nf, cudaMemcpyDeviceToHost, s));
-        CU(h, cudaMemcpyAsync(status, h->d_status, nf, cudaMemcpyDeviceToHost, s));
+        if (payload_out) CU(h, cudaMemcpyAsync(payload_out, h->hs[0].d_payload, nf * payload_stride, cudaMemcpyDeviceToHost, s));
+        if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->hs[0].d_len, nf * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+        if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->hs[0].d_rate, nf, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(status, h->hs[0].d_status, nf, cudaMemcpyDeviceToHost, s));
         if (lts1_out) CU(h, cudaMemcpyAsync(lts1_out, h->sy[li].lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     }
     CU(h, cudaStreamSynchronize(s));
@@ -813,30 +923,26 @@ int b200rx_decode_headers(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     if (!iq || !lts1_index || !avail || !status) return fail(h, B200RX_E_ARG, "b200rx_decode_headers: null argument");
     if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_decode_headers: n_frames exceeds max_frames");
     if (n_frames == 0) return B200RX_OK;
-    if (h->depth > 1) { // these entry points are not pipelined: drain the lanes, work on scratch set 0
-        int rcq = b200rx_synchronize(h);
-        if (rcq != B200RX_OK) return rcq;
-        use_lane(h, 0);
-    }
     CU(h, cudaSetDevice(h->device));
+    { int rcq = drain_lanes(h); if (rcq != B200RX_OK) return rcq; } // not pipelined: work on scratch set 0
     cudaStream_t s = h->stream;
     const size_t iq_bytes = (size_t)iq_samples * sample_bytes(h->fmt);
-    if (iq_bytes > h->d_iq_cap) {
-        if (h->d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_iq); h->d_iq = nullptr; h->d_iq_cap = 0; }
-        cudaError_t e = cudaMalloc((void **)&h->d_iq, iq_bytes);
+    if (iq_bytes > h->hs[0].d_iq_cap) {
+        if (h->hs[0].d_iq) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->hs[0].d_iq); h->hs[0].d_iq = nullptr; h->hs[0].d_iq_cap = 0; }
+        cudaError_t e = cudaMalloc((void **)&h->hs[0].d_iq, iq_bytes);
         if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_decode_headers: sample staging", e);
-        h->d_iq_cap = iq_bytes;
+        h->hs[0].d_iq_cap = iq_bytes;
     }
-    CU(h, cudaMemcpyAsync(h->d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CU(h, cudaMemcpyAsync(h->d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->hs[0].d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->hs[0].d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemcpyAsync(h->hs[0].d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     FrontendArgs fa{};
-    fa.iq = h->d_iq;
+    fa.iq = h->hs[0].d_iq;
     fa.fmt = h->fmt;
     fa.scale = h->scale;
     fa.iq_samples = iq_samples;
-    fa.lts1 = h->d_lts1;
-    fa.avail = h->d_avail;
+    fa.lts1 = h->hs[0].d_lts1;
+    fa.avail = h->hs[0].d_avail;
     fa.n_frames = n_frames;
     fa.desc = h->desc;
     fa.bm = h->bm;
@@ -845,11 +951,11 @@ int b200rx_decode_headers(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     fa.max_len = h->limits.max_payload_bytes;
     fa.header_only = 1;
     CU(h, launch_frontend(fa, s));
-    CU(h, launch_export_headers(h->desc, n_frames, h->d_len, h->d_rate, h->d_status, s));
+    CU(h, launch_export_headers(h->desc, n_frames, h->hs[0].d_len, h->hs[0].d_rate, h->hs[0].d_status, s));
     h->launches += 2;
-    if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
-    if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->d_rate, n_frames, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(status, h->d_status, n_frames, cudaMemcpyDeviceToHost, s));
+    if (payload_len) CU(h, cudaMemcpyAsync(payload_len, h->hs[0].d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+    if (rate_out) CU(h, cudaMemcpyAsync(rate_out, h->hs[0].d_rate, n_frames, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(status, h->hs[0].d_status, n_frames, cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));
     return B200RX_OK;
 }
@@ -864,12 +970,8 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
     if (max_data_bits + 6 > h->max_steps) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: trellis longer than the handle's capacity");
     if ((symbols_stride & 1) || ((uintptr_t)symbols_dev & 1)) return fail(h, B200RX_E_ARG, "b200rx_viterbi_batch_dev: symbols must be 2-byte aligned");
     if (n_frames == 0) return B200RX_OK;
-    if (h->depth > 1) { // these entry points are not pipelined: drain the lanes, work on scratch set 0
-        int rcq = b200rx_synchronize(h);
-        if (rcq != B200RX_OK) return rcq;
-        use_lane(h, 0);
-    }
     CU(h, cudaSetDevice(h->device));
+    { int rcq = drain_lanes(h); if (rcq != B200RX_OK) return rcq; } // not pipelined: work on scratch set 0
     cudaStream_t s = h->stream;
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     CU(h, cudaEventRecord(h->ev[0], s));

@@ -9,11 +9,20 @@
 // previous chunk.
 #include "rx_internal.cuh"
 
+#include <stdlib.h>
+
 namespace b200rx {
 
 namespace {
 
 constexpr int PULL_THREADS = 256;
+constexpr int PULL_BATCH = 8; // loads in flight per thread: PCIe round trips are long, keep many outstanding
+
+// index of the n-th useful sample of a frame relative to its LTS1 tag
+__device__ __forceinline__ uint32_t useful_index(uint32_t n)
+{
+    return n < 128u ? n : 128u + 80u * ((n - 128u) >> 6) + 16u + ((n - 128u) & 63u);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(PULL_THREADS) pull_kernel(const T *__restrict__ src, T *__restrict__ dst, uint64_t n_samples,
@@ -26,13 +35,21 @@ __global__ void __launch_bounds__(PULL_THREADS) pull_kernel(const T *__restrict_
         uint64_t av = avail[f];
         if (av > n_samples - p) av = n_samples - p;
         // LTS1 + LTS2 windows [0, 128), then per 80-sample slot the last 64 (fft_symbols.cpp:53-71)
-        uint32_t useful = av < 128 ? (uint32_t)av : 128u + 64u * (uint32_t)((av - 128) / 80);
+        const uint32_t useful = av < 128 ? (uint32_t)av : 128u + 64u * (uint32_t)((av - 128) / 80);
         const T *s = src + p;
         T *d = dst + p;
-#pragma unroll 4
-        for (uint32_t n = threadIdx.x; n < useful; n += PULL_THREADS) {
-            const uint32_t k = n < 128 ? n : 128u + 80u * ((n - 128u) >> 6) + 16u + ((n - 128u) & 63u);
-            d[k] = s[k];
+        for (uint32_t base = 0; base < useful; base += PULL_THREADS * PULL_BATCH) {
+            T v[PULL_BATCH];
+#pragma unroll
+            for (int u = 0; u < PULL_BATCH; u++) {
+                const uint32_t n = base + u * PULL_THREADS + threadIdx.x;
+                if (n < useful) v[u] = s[useful_index(n)];
+            }
+#pragma unroll
+            for (int u = 0; u < PULL_BATCH; u++) {
+                const uint32_t n = base + u * PULL_THREADS + threadIdx.x;
+                if (n < useful) d[useful_index(n)] = v[u];
+            }
         }
     }
 }
@@ -44,7 +61,11 @@ cudaError_t launch_pull(const void *src, void *dst, int fmt, uint64_t n_samples,
                         uint32_t n_frames, int sm_count, cudaStream_t s)
 {
     if (n_frames == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)(n_frames < (uint32_t)sm_count ? n_frames : (uint32_t)sm_count);
+    const char *e = getenv("B200RX_PULL_CTAS"); // CTAs per SM (experiments)
+    const int v = e ? atoi(e) : 0;
+    const int per_sm = v >= 1 && v <= 8 ? v : 1;
+    const uint32_t cap = (uint32_t)(sm_count * per_sm);
+    const unsigned grid = (unsigned)(n_frames < cap ? n_frames : cap);
     switch (fmt) {
         case FMT_FC64:
             pull_kernel<uint4><<<grid, PULL_THREADS, 0, s>>>((const uint4 *)src, (uint4 *)dst, n_samples, lts1, avail, n_frames);

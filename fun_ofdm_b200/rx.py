@@ -8,6 +8,7 @@ ST_OK, ST_HDR_PARITY, ST_HDR_RATE, ST_CRC_FAIL, ST_TRUNCATED, ST_TOO_LONG = rang
 ST_NO_FRAME = 255
 RATE_INVALID = 255
 FMT_FC64, FMT_FC32, FMT_SC16 = 0, 1, 2
+MAX_INFLIGHT = 3  # B200RX_MAX_INFLIGHT
 _FMT_BYTES = {FMT_FC64: 16, FMT_FC32: 8, FMT_SC16: 4}
 
 # fun::Rate -> (rate_field, cbps, dbps, bpsc)   reference src/rates.h:52-196
@@ -105,6 +106,10 @@ def load_library():
     L.b200rx_host_free.argtypes = [vp]
     L.b200rx_decode_batch.restype = C.c_int
     L.b200rx_decode_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp]
+    L.b200rx_submit_batch.restype = C.c_int
+    L.b200rx_submit_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp, C.POINTER(u64)]
+    L.b200rx_wait.restype = C.c_int
+    L.b200rx_wait.argtypes = [vp, u64]
     L.b200rx_decode_batch_dev.restype = C.c_int
     L.b200rx_decode_batch_dev.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp, C.POINTER(Debug)]
     L.b200rx_sync_dev.restype = C.c_int
@@ -257,6 +262,18 @@ class Receiver:
         rc = self.lib.b200rx_decode_batch(self.h, iq_ptr, iq_samples, lts1_ptr, avail_ptr, n, payload_ptr, stride,
                                           len_ptr, rate_ptr, status_ptr)
         self._check(rc, "b200rx_decode_batch")
+
+    def submit_batch_ptr(self, iq_ptr, iq_samples, lts1_ptr, avail_ptr, n, payload_ptr, stride, len_ptr, rate_ptr,
+                         status_ptr):
+        """Asynchronous host-buffer entry point on raw addresses; returns the ticket for wait()."""
+        t = C.c_uint64()
+        rc = self.lib.b200rx_submit_batch(self.h, iq_ptr, iq_samples, lts1_ptr, avail_ptr, n, payload_ptr, stride,
+                                          len_ptr, rate_ptr, status_ptr, C.byref(t))
+        self._check(rc, "b200rx_submit_batch")
+        return t.value
+
+    def wait(self, ticket=0):
+        self._check(self.lib.b200rx_wait(self.h, int(ticket)), "b200rx_wait")
 
     # ---- device buffers (torch tensors on this device) ----
     def decode_batch_dev(self, iq, lts1_index, avail, payload, length, rate, status, debug=None):

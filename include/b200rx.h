@@ -161,6 +161,18 @@ B200RX_API int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t iq
                         uint8_t *payload_out, uint32_t payload_stride,
                         uint16_t *payload_len, uint8_t *rate_out, uint8_t *status);
 
+/* The same call split in two, so that several batches are in flight and the PCIe link never idles: submit queues
+ * H2D + decode + D2H and returns a ticket; b200rx_wait(h, ticket) returns when that call's outputs are in the caller's
+ * arrays (ticket 0: every outstanding call).  Every buffer passed to submit - inputs and outputs - must stay valid and
+ * untouched until the wait.  At most B200RX_MAX_INFLIGHT calls overlap (a further submit first waits for the oldest);
+ * each call in flight owns a full set of device scratch.  b200rx_decode_batch == submit + wait. */
+#define B200RX_MAX_INFLIGHT 3
+B200RX_API int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
+                        const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
+                        uint8_t *payload_out, uint32_t payload_stride,
+                        uint16_t *payload_len, uint8_t *rate_out, uint8_t *status, uint64_t *ticket);
+B200RX_API int b200rx_wait(b200rx_handle *h, uint64_t ticket);
+
 /* Same contract with every array already in DEVICE memory; asynchronous on the handle's stream
  * (call b200rx_synchronize or sync the stream yourself).  dbg may be NULL. */
 B200RX_API int b200rx_decode_batch_dev(b200rx_handle *h, const void *iq_dev, uint64_t iq_samples,

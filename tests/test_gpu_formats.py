@@ -91,8 +91,8 @@ def test_pinned_host_ingest_matches_device_path(ref, rx_factory, fmt_name):
     import fun_ofdm_b200 as fo
     fmt = {"fc64": fo.FMT_FC64, "fc32": fo.FMT_FC32, "sc16": fo.FMT_SC16}[fmt_name]
     rng = np.random.default_rng(505 + fmt)
-    n = 300  # > 2 * the smallest chunk: takes the chunked pipeline
-    rx = rx_factory(512, 1500)
+    n = 600  # > 2 * the smallest chunk (256): takes the chunked pipeline
+    rx = rx_factory(640, 1500)
     rates = list(rng.integers(0, 11, n))
     lengths = list(rng.integers(0, 400, n))
     lengths[0] = 1500
@@ -150,3 +150,63 @@ def test_receive_from_sc16_capture(ref, rx_factory):
     assert np.array_equal(info_q["status"], info_wide["status"])
     assert out_q == out_wide
     assert len(out_q) >= 6
+
+
+def test_submit_wait_overlapping_calls(ref, rx_factory):
+    """b200rx_submit_batch / b200rx_wait: five different batches submitted back to back (more than B200RX_MAX_INFLIGHT, so
+    slots are reused) give exactly what one synchronous call per batch gives."""
+    import fun_ofdm_b200 as fo
+    rng = np.random.default_rng(707)
+    rx = rx_factory(640, 600)
+    lib = fo.load_library()
+    batches = []
+    for b in range(5):
+        n = 560 + 10 * b  # > 2 * 256: chunked pipeline
+        rates = list(rng.integers(0, 11, n))
+        lengths = list(rng.integers(0, 120, n))
+        batches.append(make_corpus(ref, rng, rates, lengths, snr_db=22, gap=48))
+    sync = [rx.decode_batch(c["iq"], c["lts1"], c["avail"]) for c in batches]
+
+    pinned = []
+
+    def pin(arr):
+        arr = np.ascontiguousarray(arr)
+        p = C.c_void_p()
+        assert lib.b200rx_host_alloc(C.byref(p), max(arr.nbytes, 1)) == 0
+        C.memmove(p, arr.ctypes.data, arr.nbytes)
+        pinned.append(p)
+        return p
+
+    def pin_out(nbytes):
+        p = C.c_void_p()
+        assert lib.b200rx_host_alloc(C.byref(p), nbytes) == 0
+        C.memset(p, 0xEE, nbytes)
+        pinned.append(p)
+        return p
+
+    try:
+        calls = []
+        for c in batches:
+            n = len(c["lts1"])
+            iq = pin(c["iq"])
+            l = pin(c["lts1"].astype(np.uint64))
+            a = pin(c["avail"].astype(np.uint32))
+            o = (pin_out(n * 600), pin_out(2 * n), pin_out(n), pin_out(n))
+            t = rx.submit_batch_ptr(iq, len(c["iq"]), l, a, n, o[0], 600, o[1], o[2], o[3])
+            calls.append((t, n, o))
+        assert len({t for t, _, _ in calls}) == 5
+        rx.wait(calls[2][0])  # out of order is fine
+        rx.wait(0)
+        for (t, n, o), want in zip(calls, sync):
+            payload = np.ctypeslib.as_array(C.cast(o[0], C.POINTER(C.c_uint8)), shape=(n, 600))
+            length = np.ctypeslib.as_array(C.cast(o[1], C.POINTER(C.c_uint16)), shape=(n,))
+            rate = np.ctypeslib.as_array(C.cast(o[2], C.POINTER(C.c_uint8)), shape=(n,))
+            status = np.ctypeslib.as_array(C.cast(o[3], C.POINTER(C.c_uint8)), shape=(n,))
+            assert np.array_equal(status, want[3]) and np.array_equal(rate, want[2]) and np.array_equal(length, want[1])
+            for f in range(n):
+                assert np.array_equal(payload[f, : length[f]], want[0][f, : length[f]]), f
+            assert (status == 0).sum() > n // 3
+    finally:
+        rx.wait(0)
+        for p in pinned:
+            lib.b200rx_host_free(p)
