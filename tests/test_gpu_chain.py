@@ -1,0 +1,116 @@
+"""GPU: fun::b200_receiver_chain (raw samples in, payloads out, chunk by chunk - SURVEY 8 f2) against the reference's
+own receiver_chain::process_samples (receiver_chain.cpp:106-126, compiled unmodified into oracle/_ref) on the same
+chunked stream.  Payload SEQUENCES must be identical; the GPU chain delivers a frame in the call that brings its last
+sample, the reference up to five calls later, so per-call alignment is not compared."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from test_gpu_sync import _capture
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Chain:
+    def __init__(self, max_frames=256, max_payload=4095):
+        self.lib = C.CDLL(os.path.join(ROOT, "fun_ofdm_b200", "lib", "libb200host.so"))
+        self.lib.b200host_chain_new.restype = C.c_void_p
+        self.lib.b200host_chain_new.argtypes = [C.c_int, C.c_uint, C.c_uint]
+        self.lib.b200host_chain_process.restype = C.c_int
+        self.lib.b200host_chain_process.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self.lib.b200host_chain_delete.argtypes = [C.c_void_p]
+        self.lib.b200host_chain_counters.argtypes = [C.c_void_p, C.c_void_p]
+        self.h = self.lib.b200host_chain_new(0, max_frames, max_payload)
+        assert self.h, "b200_receiver_chain could not be created (no GPU?)"
+
+    def process(self, samples, max_out=512, stride=4095):
+        """samples=None: flush"""
+        payload = np.zeros((max_out, stride), np.uint8)
+        length = np.zeros(max_out, np.int32)
+        if samples is None:
+            n = self.lib.b200host_chain_process(self.h, None, -1, payload.ctypes.data, stride, length.ctypes.data, max_out)
+        else:
+            iq = np.ascontiguousarray(samples, dtype=np.complex128).view(np.float64)
+            n = self.lib.b200host_chain_process(self.h, iq.ctypes.data, len(iq) // 2, payload.ctypes.data, stride,
+                                                length.ctypes.data, max_out)
+        assert n <= max_out
+        return [bytes(payload[i, : length[i]]) for i in range(n)]
+
+    def counters(self):
+        c = np.zeros(7, np.uint64)
+        self.lib.b200host_chain_counters(self.h, c.ctypes.data)
+        return dict(zip(["samples", "calls", "found", "ok", "crc_fail", "headers_bad", "truncated"], (int(x) for x in c)))
+
+    def close(self):
+        self.lib.b200host_chain_delete(self.h)
+
+
+def _reference_chain(ref, x, chunk):
+    chain = ref.chain_new()
+    out = []
+    for s in range(0, len(x), chunk):
+        out += ref.chain_process(chain, x[s: s + chunk])
+    for _ in range(8):  # drain the six-stage pipeline (one round per block)
+        out += ref.chain_process(chain, np.zeros(chunk, complex))
+    return out
+
+
+@pytest.mark.parametrize("chunk", [4096, 1000, 333])
+@pytest.mark.parametrize("snr", [28, 16])
+def test_chunked_stream_matches_reference_chain(ref, chunk, snr):
+    rng = np.random.default_rng(900 + chunk + snr)
+    rates = [10, 8, 0, 5, 10, 3, 9, 6, 10, 2, 1, 4, 7, 10]
+    lengths = [1500, 300, 40, 700, 64, 1000, 1499, 255, 0, 120, 77, 410, 900, 333]
+    x, payloads = _capture(ref, rng, rates, lengths, snr, gap=500, lead=300, tail=4096)
+    want = _reference_chain(ref, x, chunk)
+    ch = Chain()
+    got = []
+    for s in range(0, len(x), chunk):
+        got += ch.process(x[s: s + chunk])
+    got += ch.process(None)
+    c = ch.counters()
+    ch.close()
+    assert got == want, (len(got), len(want), c)
+    assert len(got) >= (len(rates) - 3 if snr >= 25 else 3), c
+    assert c["samples"] >= len(x)
+
+
+def test_loopback_config1(ref):
+    """BASELINE config 1 = examples/test_sim.cpp:43-104: RATE_3_4_QAM16, the 100-character string x 15 = 1500 bytes, 100
+    identical frames concatenated back to back, noiseless, a zero pad behind them, fed in 4096-sample chunks.  The
+    reference chain and the GPU chain must return the same payload sequence (test_sim prints `Received N packets`)."""
+    data = b"I'm a little tea pot, short and stout.....here is my handle.....blah blah blah.....this rhyme sucks!"
+    assert len(data) == 100
+    payload = data * 15
+    frame = ref.build_frame(payload, 8)
+    x = np.concatenate([frame] * 100 + [np.zeros(10 * len(frame), complex)])
+    want = _reference_chain(ref, x, 4096)
+    ch = Chain()
+    got = []
+    for s in range(0, len(x), 4096):
+        got += ch.process(x[s: s + 4096])
+    got += ch.process(None)
+    c = ch.counters()
+    ch.close()
+    assert got == want, (len(got), len(want), c)
+    assert len(got) >= 99 and all(g == payload for g in got)
+
+
+def test_one_long_call_equals_many_short_ones(ref):
+    rng = np.random.default_rng(31)
+    rates = [int(r) for r in rng.integers(0, 11, 40)]
+    lengths = [int(v) for v in rng.integers(0, 600, 40)]
+    x, _ = _capture(ref, rng, rates, lengths, 24, gap=420, lead=300, tail=2048)
+    a = Chain()
+    one = a.process(x) + a.process(None)
+    a.close()
+    b = Chain()
+    many = []
+    for s in range(0, len(x), 2500):
+        many += b.process(x[s: s + 2500])
+    many += b.process(None)
+    b.close()
+    assert one == many and len(one) >= 30
