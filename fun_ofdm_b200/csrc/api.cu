@@ -72,7 +72,7 @@ struct b200rx_handle {
         uint64_t *ev_x = nullptr;
         uint32_t *ev_count = nullptr;
         SyncRec *rec = nullptr;
-        uint32_t *order = nullptr;
+        CtaEvents *cta_ev = nullptr; uint8_t *cta_cnt = nullptr; uint32_t cta_cap = 0;
         uint64_t *lts1 = nullptr;
         uint32_t *avail = nullptr;
         FrameRot *rot = nullptr;
@@ -298,7 +298,7 @@ int b200rx_destroy(b200rx_handle *h)
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (auto &y : h->sy) {
-        cudaFree(y.ev_x); cudaFree(y.ev_count); cudaFree(y.rec); cudaFree(y.order); cudaFree(y.lts1);
+        cudaFree(y.ev_x); cudaFree(y.ev_count); cudaFree(y.rec); cudaFree(y.cta_ev); cudaFree(y.cta_cnt); cudaFree(y.lts1);
         cudaFree(y.avail); cudaFree(y.rot); cudaFree(y.phase); cudaFree(y.summary);
     }
     if (h->sy_summary_host) cudaFreeHost(h->sy_summary_host);
@@ -750,9 +750,8 @@ int ensure_sync_scratch(b200rx_handle *h, int lane)
     if (e == cudaSuccess && !y.summary) {
         auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
         A((void **)&y.ev_x, h->sy_ev_cap * sizeof(uint64_t));
-        A((void **)&y.ev_count, sizeof(uint32_t));
+        A((void **)&y.ev_count, 2 * sizeof(uint32_t));
         A((void **)&y.rec, h->sy_ev_cap * sizeof(SyncRec));
-        A((void **)&y.order, h->sy_ev_cap * sizeof(uint32_t));
         A((void **)&y.lts1, nf * sizeof(uint64_t));
         A((void **)&y.avail, nf * sizeof(uint32_t));
         A((void **)&y.rot, nf * sizeof(FrameRot));
@@ -769,7 +768,19 @@ int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const void *iq_
 {
     int rc = ensure_sync_scratch(h, lane);
     if (rc != B200RX_OK) return rc;
-    const b200rx_handle::SyncScratch &y = h->sy[lane];
+    b200rx_handle::SyncScratch &y = h->sy[lane];
+    const uint32_t n_ctas = sync_cta_count(n_samples);
+    if (n_ctas > y.cta_cap) { // grow-only; work queued on this lane's stream may still read the old list
+        if (y.cta_ev) {
+            CU(h, cudaStreamSynchronize(s));
+            cudaFree(y.cta_ev); cudaFree(y.cta_cnt);
+            y.cta_ev = nullptr; y.cta_cnt = nullptr; y.cta_cap = 0;
+        }
+        cudaError_t e = cudaMalloc((void **)&y.cta_ev, (size_t)n_ctas * sizeof(CtaEvents));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&y.cta_cnt, n_ctas);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "sync scratch (detector event lists)", e);
+        y.cta_cap = n_ctas;
+    }
     SyncArgs a{};
     a.iq = iq_dev;
     a.fmt = h->fmt;
@@ -779,11 +790,11 @@ int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const void *iq_
     a.max_frames = h->limits.max_frames;
     a.tags = tags_dev;
     a.ev_x = y.ev_x; a.ev_count = y.ev_count; a.ev_cap = h->sy_ev_cap;
-    a.rec = y.rec; a.order = y.order;
+    a.rec = y.rec; a.cta_ev = y.cta_ev; a.cta_cnt = y.cta_cnt;
     a.lts1 = y.lts1; a.avail = y.avail; a.rot = y.rot; a.phase = y.phase;
     a.summary = y.summary;
     CU(h, launch_sync(a, s));
-    h->launches += n_samples ? 4 : 1;
+    h->launches += n_samples ? 4 : 1; // detect, scan, lts_sync, build_frames
     return B200RX_OK;
 }
 

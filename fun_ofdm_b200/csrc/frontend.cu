@@ -17,6 +17,7 @@
 // All arithmetic before the quantiser is fp64 like the reference.
 #include "rx_internal.cuh"
 #include "viterbi_core.cuh"
+#include "fft64.cuh"
 
 #include <math.h>
 
@@ -32,7 +33,6 @@ constexpr int ERASURE_AT = 288;
 // i.e. depuncture (puncturer.cpp:94-118) composed with deinterleave (interleaver.cpp:31-37); ERASURE_AT marks a
 // re-inserted erasure (value 127).  Filled by upload_frontend_tables from step_index_pair() below.
 __constant__ uint32_t c_step_idx[11][216];
-constexpr unsigned FULL = 0xFFFFFFFFu;
 
 __constant__ double2 c_twiddle[64];  // exp(-2 pi i k / 64)
 __constant__ int8_t c_polarity[127]; // pilot polarity sequence (phase_tracker.cpp:23-32)
@@ -43,46 +43,7 @@ __constant__ int8_t c_polarity[127]; // pilot polarity sequence (phase_tracker.c
 constexpr unsigned long long LTS_NONZERO = 0x07FFFFFEFFFFFFC0ull;
 constexpr unsigned long long LTS_NEG = 0x00567D4C0A605300ull;
 
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 cmul(double2 a, double2 b)
-{
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 shfl_xor2(double2 v, int m)
-{
-    return make_double2(__shfl_xor_sync(FULL, v.x, m), __shfl_xor_sync(FULL, v.y, m));
-}
-
-// 64-point forward DFT of (v0, v1) = (x[lane], x[lane + 32]).  On return lane holds
-// X[k0] in v0 and X[k1] in v1 with k = bitrev6((lane << 1) | slot); in the reference's shifted
-// storage (fft.cpp:20-24: data[s] = X[(s + 32) % 64]) that is s = ((slot ^ 1) << 5) | bitrev5(lane).
-__device__ __forceinline__ void warp_fft64(double2 &v0, double2 &v1, const double2 *tw, int lane)
-{
-    double2 a = v0, b = v1;
-    v0 = cadd(a, b);
-    v1 = cmul(csub(a, b), tw[lane]);
-#pragma unroll
-    for (int bb = 4; bb >= 0; --bb) {
-        const int S = 1 << bb;
-        const bool hi = (lane & S) != 0;
-        const double2 send = hi ? v0 : v1;
-        const double2 recv = shfl_xor2(send, S);
-        a = hi ? recv : v0;
-        b = hi ? v1 : recv;
-        v0 = cadd(a, b);
-        const double2 d = csub(a, b);
-        v1 = (bb > 0) ? cmul(d, tw[(lane & (S - 1)) << (5 - bb)]) : d;
-    }
-}
-
 __device__ __forceinline__ int shifted_index(int lane, int slot) { return ((slot ^ 1) << 5) | (int)(__brev((unsigned)lane) >> 27); }
-
-// 48 data carriers in ascending bin order (phase_tracker.cpp:46-50): 6..58 without 11, 25, 32, 39, 53
-__device__ __forceinline__ int data_bin(int c)
-{
-    return c + 6 + (c >= 5) + (c >= 18) + (c >= 24) + (c >= 30) + (c >= 43);
-}
 
 // QAM<N>::decode (qam.h:110-125) for one axis: pt = (int)(x * scale) truncates toward zero
 template <int NBITS>

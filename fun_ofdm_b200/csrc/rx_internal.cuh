@@ -135,6 +135,12 @@ struct FrameRot {     // constant rotation timing_sync applies to the samples of
     uint64_t from;    // stream index of the frame's STS_END tag
 };
 
+struct CtaEvents {    // STS_END tags one detector CTA found, in stream order (offsets within the CTA's range)
+    enum { CAP = 15 };
+    uint16_t count;   // all found, even if more than CAP
+    uint16_t off[CAP];
+};
+
 typedef b200rx_sync_result SyncSummary;
 
 struct SyncArgs {
@@ -145,11 +151,12 @@ struct SyncArgs {
     double2 rot_in;       // (cos, sin) of m_phase_acc before the stream
     uint32_t max_frames;
     uint8_t *tags;        // [n_samples] or null
-    uint64_t *ev_x;       // scratch [ev_cap]
-    uint32_t *ev_count;   // scratch
+    CtaEvents *cta_ev;    // scratch [sync_cta_count(n_samples)]
+    uint8_t *cta_cnt;     // scratch [sync_cta_count(n_samples)]: events per detector CTA (saturating)
+    uint64_t *ev_x;       // scratch [ev_cap]: STS_END positions in stream order
+    uint32_t *ev_count;   // scratch [2]: events kept, events lost
     uint32_t ev_cap;
     SyncRec *rec;         // scratch [ev_cap]
-    uint32_t *order;      // scratch [ev_cap]
     uint64_t *lts1;       // [max_frames]
     uint32_t *avail;      // [max_frames]
     FrameRot *rot;        // [max_frames]
@@ -158,6 +165,7 @@ struct SyncArgs {
 };
 
 cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s);
+uint32_t sync_cta_count(uint64_t n_samples);
 cudaError_t upload_sync_tables();
 
 // ---- launchers (each returns the cudaError_t of the launch) ----

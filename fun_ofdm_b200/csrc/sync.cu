@@ -33,71 +33,187 @@ namespace {
 
 __constant__ double2 c_lts_conj[64];
 
-constexpr int DT = 512;          // samples per detector CTA
-constexpr int DET_THREADS = 256;
+constexpr int DET_THREADS = 128;
+constexpr int DET_PER_THREAD = 8;                       // flags per thread
+constexpr int DET_FLAGS = DET_THREADS * DET_PER_THREAD; // flags per CTA: stream indices t0 - 16 .. t0 + DT - 1
+constexpr int DT = DET_FLAGS - 16;                      // tags per CTA
+constexpr int DET_PRODUCTS = DET_FLAGS + 15;            // products of stream indices t0 - 31 .. t0 + DT - 1
+constexpr int DET_SAMPLES = DET_PRODUCTS + 16;          // samples of stream indices t0 - 47 .. t0 + DT - 1
 constexpr double PLATEAU_THRESHOLD = 0.9; // frame_detector.h:12
 constexpr double LTS_CORR_THRESHOLD = 0.9; // timing_sync.h:12
 
 enum : uint8_t { TAG_NONE = 0, TAG_STS_START = 1, TAG_STS_END = 2, TAG_LTS1 = 4, TAG_LTS2 = 5 }; // tagged_vector.h:25-34
 
+// one padding slot per 8 entries: a thread's 23 consecutive window entries start 8 apart from its neighbour's, and a
+// stride of 9 doubles keeps the 16 lanes of a half warp on distinct banks
+__device__ __forceinline__ int pad8(int q) { return q + (q >> 3); }
+
+// sum of the 16 products ending at each of 8 consecutive positions: w[j] = p[j] + ... + p[j + 15], j = 0..7, from 23
+// inputs by doubling (pairs, fours, eights, sixteens): 66 additions instead of 120
+__device__ __forceinline__ void window16(const double *src, double (&w)[DET_PER_THREAD])
+{
+    double a[23];
+#pragma unroll
+    for (int k = 0; k < 23; k++) a[k] = src[pad8(k) - 0];
+#pragma unroll
+    for (int k = 0; k < 22; k++) a[k] = __dadd_rn(a[k], a[k + 1]);
+#pragma unroll
+    for (int k = 0; k < 20; k++) a[k] = __dadd_rn(a[k], a[k + 2]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = __dadd_rn(a[k], a[k + 4]);
+#pragma unroll
+    for (int k = 0; k < DET_PER_THREAD; k++) w[k] = __dadd_rn(a[k], a[k + 8]);
+}
+
+// frame_detector::work (frame_detector.cpp:41-92).  Per CTA DT tags; per thread 8 plateau flags.
 template <int FMT>
 __global__ void __launch_bounds__(DET_THREADS) detect_kernel(const void *iq, double scale, uint64_t n, uint8_t *tags,
-                                                             uint64_t *ev_x, uint32_t *ev_count, uint32_t ev_cap,
-                                                             uint64_t x_limit)
+                                                             CtaEvents *cta_ev, uint8_t *cta_cnt, uint64_t x_limit)
 {
-    __shared__ double2 s_s[DT + 48];
-    __shared__ double2 s_c[DT + 32];
-    __shared__ double s_p[DT + 32];
-    __shared__ uint8_t s_f[DT + 16];
+    __shared__ double s_re[DET_SAMPLES], s_im[DET_SAMPLES];
+    __shared__ uint32_t s_nev;
+    __shared__ uint16_t s_ev[CtaEvents::CAP];
+    __shared__ double s_cr[DET_PRODUCTS + DET_PRODUCTS / 8 + 8], s_ci[DET_PRODUCTS + DET_PRODUCTS / 8 + 8],
+        s_pw[DET_PRODUCTS + DET_PRODUCTS / 8 + 8];
+    __shared__ uint32_t s_bits[DET_FLAGS / 32 + 1];
     const int tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * DT;
 
-    for (int k = tid; k < DT + 48; k += DET_THREADS) {
-        const int64_t i = t0 - 48 + k;
-        s_s[k] = (i >= 0 && (uint64_t)i < n) ? load_sample<FMT>(iq, (uint64_t)i, scale) : make_double2(0.0, 0.0); // the carry-over starts as zeros (frame_detector.cpp:27)
+    {
+        // all of a thread's loads are issued before the first use: one HBM round trip per tile, not nine
+        constexpr int PER = (DET_SAMPLES + DET_THREADS - 1) / DET_THREADS;
+        double2 v[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int k = tid + u * DET_THREADS;
+            const int64_t i = t0 - 47 + k;
+            // the carry-over starts as zeros (frame_detector.cpp:27)
+            v[u] = (k < DET_SAMPLES && i >= 0 && (uint64_t)i < n) ? load_sample<FMT>(iq, (uint64_t)i, scale) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int k = tid + u * DET_THREADS;
+            if (k < DET_SAMPLES) { s_re[k] = v[u].x; s_im[k] = v[u].y; }
+        }
     }
+    if (tid <= DET_FLAGS / 32) s_bits[tid] = 0;
+    if (tid == 0) s_nev = 0;
     __syncthreads();
-    // products of stream index t0 - 32 + j
-    for (int j = tid; j < DT + 32; j += DET_THREADS) {
-        const double2 a = s_s[j + 16], d = s_s[j];
-        // input * std::conj(delayed): (a.x + i a.y)(d.x - i d.y)
-        double cr = __dadd_rn(__dmul_rn(a.x, d.x), __dmul_rn(a.y, d.y));
-        double ci = __dsub_rn(__dmul_rn(a.y, d.x), __dmul_rn(a.x, d.y));
-        double pw = __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y)); // std::norm
+    // product q belongs to stream index t0 - 31 + q: input * conj(input delayed by 16), and the input's power
+    for (int q = tid; q < DET_PRODUCTS; q += DET_THREADS) {
+        const double ax = s_re[q + 16], ay = s_im[q + 16], dx = s_re[q], dy = s_im[q];
+        double cr = __dadd_rn(__dmul_rn(ax, dx), __dmul_rn(ay, dy));
+        double ci = __dsub_rn(__dmul_rn(ay, dx), __dmul_rn(ax, dy));
+        double pw = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)); // std::norm
         if (cr != cr || ci != ci) { cr = 0.0; ci = 0.0; } // circular_accumulator.h:90
         if (pw != pw) pw = 0.0;
-        s_c[j] = make_double2(cr, ci);
-        s_p[j] = pw;
+        const int o = pad8(q);
+        s_cr[o] = cr;
+        s_ci[o] = ci;
+        s_pw[o] = pw;
     }
     __syncthreads();
-    // flag of stream index t0 - 16 + j: window = products j + 1 .. j + 16
-    for (int j = tid; j < DT + 16; j += DET_THREADS) {
-        double cr = 0.0, ci = 0.0, pw = 0.0;
+    // flags of stream indices t0 - 16 + 8 * tid + (0..7): |C| / P > 0.9 as |C|^2 > (0.9 P)^2 (P >= 0; 0/0 is no plateau)
+    {
+        const int o = pad8(DET_PER_THREAD * tid); // multiple of 9: pad8(8 tid + k) = o + pad8(k)
+        double wr[DET_PER_THREAD], wi[DET_PER_THREAD], wp[DET_PER_THREAD];
+        window16(s_cr + o, wr);
+        window16(s_ci + o, wi);
+        window16(s_pw + o, wp);
+        uint32_t mask = 0;
 #pragma unroll
-        for (int k = 1; k <= 16; k++) {
-            cr = __dadd_rn(cr, s_c[j + k].x);
-            ci = __dadd_rn(ci, s_c[j + k].y);
-            pw = __dadd_rn(pw, s_p[j + k]);
+        for (int k = 0; k < DET_PER_THREAD; k++) {
+            const double t = PLATEAU_THRESHOLD * wp[k];
+            const double m2 = wr[k] * wr[k] + wi[k] * wi[k];
+            if (m2 > t * t) mask |= 1u << k;
         }
-        const double corr = hypot(cr, ci) / pw;
-        s_f[j] = corr > PLATEAU_THRESHOLD ? 1 : 0;
+        if (mask) atomicOr(&s_bits[tid >> 2], mask << (8 * (tid & 3)));
     }
     __syncthreads();
+    // tag of stream index t0 + m from the flags of t0 + m - 16 .. t0 + m = flag bits m .. m + 16
     for (int m = tid; m < DT; m += DET_THREADS) {
         const int64_t i = t0 + m;
         if ((uint64_t)i >= n) break;
-        int run = 0; // flags of i-15 .. i-1
-#pragma unroll
-        for (int k = 1; k <= 15; k++) run += s_f[m + k];
-        const int f_old = s_f[m], f_now = s_f[m + 16];
+        const uint32_t w = __funnelshift_r(s_bits[m >> 5], s_bits[(m >> 5) + 1], m & 31) & 0x1FFFFu;
         uint8_t tag = TAG_NONE;
-        if (f_now && run == 15 && !f_old) tag = TAG_STS_START;  // plateau length reaches 16 exactly here
-        else if (!f_now && run == 15 && f_old) tag = TAG_STS_END; // first clear flag after a run of >= 16
+        if (w == 0x1FFFEu) tag = TAG_STS_START;     // 16 flags in a row ending here, none before: plateau length reaches 16
+        else if (w == 0x0FFFFu) tag = TAG_STS_END;  // first clear flag after a run of >= 16
         if (tags) tags[i] = tag;
         if (tag == TAG_STS_END && (uint64_t)i < x_limit) {
-            const uint32_t slot = atomicAdd(ev_count, 1u);
-            if (slot < ev_cap) ev_x[slot] = (uint64_t)i;
+            const uint32_t slot = atomicAdd(&s_nev, 1u);
+            if (slot < CtaEvents::CAP) s_ev[slot] = (uint16_t)m;
         }
+    }
+    __syncthreads();
+    // this CTA's STS_END tags in stream order (a tag needs 16 set flags in front of it, so at most DT / 17 per CTA; more
+    // than CAP only in pathological streams - the excess is counted, not kept)
+    if (tid == 0) {
+        const uint32_t cnt = s_nev, kept = cnt < CtaEvents::CAP ? cnt : CtaEvents::CAP;
+        cta_cnt[blockIdx.x] = (uint8_t)(cnt < 255 ? cnt : 255);
+        if (cnt == 0) return; // the list of a CTA without events is never read
+        CtaEvents out;
+        out.count = (uint16_t)cnt;
+        for (uint32_t a = 0; a < CtaEvents::CAP; a++) out.off[a] = 0xFFFF;
+        for (uint32_t a = 0; a < kept; a++) { // insertion sort, kept is 0 or 1 almost always
+            const uint16_t v = s_ev[a];
+            uint32_t b = a;
+            while (b > 0 && out.off[b - 1] > v) { out.off[b] = out.off[b - 1]; b--; }
+            out.off[b] = v;
+        }
+        cta_ev[blockIdx.x] = out;
+    }
+}
+
+// Per-CTA lists -> one list of STS_END positions in stream order (one CTA; exclusive scan of the per-CTA counts).
+// ev_count[0] = events kept, ev_count[1] = events lost (beyond ev_cap, or beyond a detector CTA's list).
+constexpr int SCAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_events_kernel(const CtaEvents *cta_ev, const uint8_t *cta_cnt, uint32_t n_ctas,
+                                                                   uint64_t *ev_x, uint32_t *ev_count, uint32_t ev_cap)
+{
+    __shared__ uint32_t s_warp[32], s_lost[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n_ctas + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint32_t c0 = min(n_ctas, tid * per), c1 = min(n_ctas, c0 + per);
+    uint32_t mine = 0, lost = 0;
+    for (uint32_t c = c0; c < c1; c++) {
+        const uint32_t cnt = cta_cnt[c];
+        mine += min(cnt, (uint32_t)CtaEvents::CAP);
+        lost += cnt > CtaEvents::CAP ? cnt - CtaEvents::CAP : 0u;
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    lost = __reduce_add_sync(0xFFFFFFFFu, lost);
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_lost[warp] = lost;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        s_warp[lane] = wi - w; // exclusive offset of each warp
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
+        const uint32_t lost_all = __reduce_add_sync(0xFFFFFFFFu, s_lost[lane]);
+        if (lane == 0) {
+            ev_count[0] = min(total, ev_cap);
+            ev_count[1] = lost_all + (total > ev_cap ? total - ev_cap : 0u);
+        }
+    }
+    __syncthreads();
+    uint32_t pos = s_warp[warp] + incl - mine;
+    for (uint32_t c = c0; c < c1; c++) {
+        if (cta_cnt[c] == 0) continue;
+        const CtaEvents e = cta_ev[c];
+        const uint32_t kept = min((uint32_t)e.count, (uint32_t)CtaEvents::CAP);
+        for (uint32_t a = 0; a < kept; a++, pos++)
+            if (pos < ev_cap) ev_x[pos] = (uint64_t)c * DT + e.off[a];
     }
 }
 
@@ -110,7 +226,7 @@ __global__ void __launch_bounds__(128) lts_sync_kernel(const void *iq, double sc
     __shared__ double2 s_s[160];
     __shared__ double s_val[96];
     const int tid = threadIdx.x;
-    const uint32_t n_ev = min(*ev_count, ev_cap);
+    const uint32_t n_ev = min(ev_count[0], ev_cap);
     for (uint32_t e = blockIdx.x; e < n_ev; e += gridDim.x) {
         const uint64_t x = ev_x[e];
         __syncthreads();
@@ -177,73 +293,71 @@ __global__ void __launch_bounds__(128) lts_sync_kernel(const void *iq, double sc
     }
 }
 
-// Rank of every event by stream position (x values are distinct: one tag per sample): order[rank] = event.
-__global__ void __launch_bounds__(256) rank_events_kernel(const SyncRec *rec, const uint32_t *ev_count, uint32_t ev_cap,
-                                                          uint32_t *order)
-{
-    __shared__ uint64_t s_x[256];
-    const uint32_t E = min(*ev_count, ev_cap);
-    const uint32_t e = blockIdx.x * 256 + threadIdx.x;
-    if (blockIdx.x * 256 >= E) return;
-    const uint64_t x = e < E ? rec[e].x : 0;
-    uint32_t rank = 0;
-    for (uint32_t base = 0; base < E; base += 256) {
-        __syncthreads();
-        s_x[threadIdx.x] = (base + threadIdx.x < E) ? rec[base + threadIdx.x].x : ~0ull;
-        __syncthreads();
-        const uint32_t m = min(256u, E - base);
-        for (uint32_t k = 0; k < m; k++) rank += s_x[k] < x;
-    }
-    if (e < E) order[rank] = e;
-}
-
 // Events -> frames in stream order (one CTA).  Frame k starts at the LTS1 tag of the k-th successful event;
 // it owns the samples up to the next LTS1 tag (fft_symbols.cpp:42-51 restarts there).
 constexpr int BF_THREADS = 1024;
 
 __global__ void __launch_bounds__(BF_THREADS) build_frames_kernel(const SyncRec *rec, const uint32_t *ev_count, uint32_t ev_cap,
                                                                   uint64_t n, double2 rot_in, uint32_t max_frames,
-                                                                  uint32_t *order, uint64_t *lts1, uint32_t *avail, FrameRot *rot,
+                                                                  uint64_t *lts1, uint32_t *avail, FrameRot *rot,
                                                                   double *phase, uint8_t *tags, SyncSummary *summary)
 {
-    __shared__ uint32_t s_part[BF_THREADS];
+    __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
-    const int tid = threadIdx.x;
-    const uint32_t n_all = *ev_count;
-    const uint32_t E = min(n_all, ev_cap);
-    // is sorted event k the start of a new frame?  (found, and not the same LTS1 as the previous found event)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t E = min(ev_count[0], ev_cap); // events kept, in stream order
+    const uint32_t n_lost = ev_count[1];
+    // is event k the start of a new frame?  (found, and not the same LTS1 as the previous found event)
     auto is_frame = [&](uint32_t k) -> bool {
-        const SyncRec &r = rec[order[k]];
+        const SyncRec &r = rec[k];
         if (!r.found || r.lts1 < 0 || (uint64_t)r.lts1 >= n) return false;
         for (int64_t q = (int64_t)k - 1; q >= 0; q--) {
-            const SyncRec &pr = rec[order[q]];
+            const SyncRec &pr = rec[q];
             if (pr.found) return pr.lts1 != r.lts1;
         }
         return true;
     };
-    const uint32_t per = (E + BF_THREADS - 1) / BF_THREADS;
+    const uint32_t per = (E + BF_THREADS - 1) / BF_THREADS; // <= 8 for the usual ev_cap: one bit per event
     const uint32_t k0 = min(E, tid * per), k1 = min(E, k0 + per);
     uint32_t cnt = 0;
-    for (uint32_t k = k0; k < k1; k++) cnt += is_frame(k) ? 1u : 0u;
-    s_part[tid] = cnt;
+    uint64_t frame_bits = 0; // is_frame of events k0 .. k0 + 63 (per > 64 falls back to re-evaluation)
+    for (uint32_t k = k0; k < k1; k++) {
+        const bool f = is_frame(k);
+        cnt += f ? 1u : 0u;
+        if (f && k - k0 < 64) frame_bits |= 1ull << (k - k0);
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (tid == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < BF_THREADS; i++) { const uint32_t c = s_part[i]; s_part[i] = run; run += c; }
-        s_total = run;
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_total = wi;
     }
     __syncthreads();
-    uint32_t idx = s_part[tid];
+    uint32_t idx = s_warp[warp] + incl - cnt;
     for (uint32_t k = k0; k < k1; k++) {
-        if (!is_frame(k)) continue;
-        const SyncRec &r = rec[order[k]];
+        const bool f = (k - k0 < 64) ? ((frame_bits >> (k - k0)) & 1ull) != 0 : is_frame(k);
+        if (!f) continue;
+        const SyncRec &r = rec[k];
         if (idx < max_frames) {
             lts1[idx] = (uint64_t)r.lts1;
             FrameRot fr;
             fr.rot_new = r.rot;
             fr.rot_old = rot_in;
             for (int64_t q = (int64_t)k - 1; q >= 0; q--) {
-                const SyncRec &pr = rec[order[q]];
+                const SyncRec &pr = rec[q];
                 if (pr.found) { fr.rot_old = pr.rot; break; }
             }
             fr.from = r.x;
@@ -252,7 +366,7 @@ __global__ void __launch_bounds__(BF_THREADS) build_frames_kernel(const SyncRec 
             // samples until the next frame's LTS1 (or the end of the stream)
             uint64_t end = n;
             for (uint32_t q = k + 1; q < E; q++) {
-                const SyncRec &nr = rec[order[q]];
+                const SyncRec &nr = rec[q];
                 if (nr.found && nr.lts1 != r.lts1) { if (nr.lts1 > r.lts1 && (uint64_t)nr.lts1 < n) end = (uint64_t)nr.lts1; break; }
             }
             const uint64_t span = end - (uint64_t)r.lts1;
@@ -264,17 +378,16 @@ __global__ void __launch_bounds__(BF_THREADS) build_frames_kernel(const SyncRec 
         }
         idx++;
     }
-    __syncthreads();
     if (tid == 0) {
-        summary->n_events = n_all;
+        summary->n_events = E + n_lost;
         summary->n_frames = min(s_total, max_frames);
-        summary->overflow = (n_all > ev_cap ? n_all - ev_cap : 0u) + (s_total > max_frames ? s_total - max_frames : 0u);
+        summary->overflow = n_lost + (s_total > max_frames ? s_total - max_frames : 0u);
         summary->reserved = 0;
         // m_phase_acc after the stream: the last successful event's
         double ph = 0.0;
         int have = 0;
         for (int64_t q = (int64_t)E - 1; q >= 0; q--) {
-            const SyncRec &pr = rec[order[q]];
+            const SyncRec &pr = rec[q];
             if (pr.found) { ph = pr.phase; have = 1; break; }
         }
         summary->last_phase = ph;
@@ -303,35 +416,37 @@ cudaError_t upload_sync_tables()
     return cudaMemcpyToSymbol(c_lts_conj, tab, sizeof(tab));
 }
 
+uint32_t sync_cta_count(uint64_t n_samples) { return (uint32_t)((n_samples + DT - 1) / DT); }
+
 cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s)
 {
-    cudaError_t e = cudaMemsetAsync(a.ev_count, 0, sizeof(uint32_t), s);
+    cudaError_t e = cudaMemsetAsync(a.ev_count, 0, 2 * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     if (a.n_samples > 0) {
-        const uint64_t blocks = (a.n_samples + DT - 1) / DT;
+        const unsigned blocks = sync_cta_count(a.n_samples);
         const uint64_t x_limit = a.n_samples > 160 ? a.n_samples - 160 : 0; // timing_sync.cpp:68: x < input.size() - CARRYOVER_LENGTH
         switch (a.fmt) {
-            case FMT_FC64:
-                detect_kernel<FMT_FC64><<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
-                lts_sync_kernel<FMT_FC64><<<a.ev_cap, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
-                break;
-            case FMT_FC32:
-                detect_kernel<FMT_FC32><<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
-                lts_sync_kernel<FMT_FC32><<<a.ev_cap, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
-                break;
-            case FMT_SC16:
-                detect_kernel<FMT_SC16><<<(unsigned)blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.ev_x, a.ev_count, a.ev_cap, x_limit);
-                lts_sync_kernel<FMT_SC16><<<a.ev_cap, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec);
-                break;
+            case FMT_FC64: detect_kernel<FMT_FC64><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit); break;
+            case FMT_FC32: detect_kernel<FMT_FC32><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit); break;
+            case FMT_SC16: detect_kernel<FMT_SC16><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit); break;
             default: return cudaErrorInvalidValue;
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        rank_events_kernel<<<(a.ev_cap + 255) / 256, 256, 0, s>>>(a.rec, a.ev_count, a.ev_cap, a.order);
+        scan_events_kernel<<<1, SCAN_THREADS, 0, s>>>(a.cta_ev, a.cta_cnt, blocks, a.ev_x, a.ev_count, a.ev_cap);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // enough CTAs for one event each at the usual rates; the kernel strides over the rest
+        const unsigned lts_grid = a.ev_cap < 4096u ? a.ev_cap : 4096u;
+        switch (a.fmt) {
+            case FMT_FC64: lts_sync_kernel<FMT_FC64><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec); break;
+            case FMT_FC32: lts_sync_kernel<FMT_FC32><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec); break;
+            default: lts_sync_kernel<FMT_SC16><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec); break;
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    build_frames_kernel<<<1, BF_THREADS, 0, s>>>(a.rec, a.ev_count, a.ev_cap, a.n_samples, a.rot_in, a.max_frames, a.order,
+    build_frames_kernel<<<1, BF_THREADS, 0, s>>>(a.rec, a.ev_count, a.ev_cap, a.n_samples, a.rot_in, a.max_frames,
                                                  a.lts1, a.avail, a.rot, a.phase, a.tags, a.summary);
     return cudaGetLastError();
 }

@@ -117,3 +117,52 @@ def build_corpus(payloads, rates, snr_db=25.0, multipath_taps=0, lead_in=0, seed
     lts1 = off + np.uint64(lead_in + LTS1_OFFSET)
     avail = (ns - np.uint64(LTS1_OFFSET)).astype(np.uint32)
     return dict(iq=out[:total], lts1=lts1, avail=avail, frame_off=off, lengths=lengths, rates=rates)
+
+
+def build_corpus_dev(payloads, rates, snr_db=25.0, multipath_taps=0, lead_in=0, seed=0xB200, device=0, stream=None):
+    """build_corpus on the GPU (b200tx_build_batch_dev in libb200rx.so, fun_ofdm_b200/csrc/txgen.cu): the stream is
+    written straight into HBM.  Same arguments, same layout, same seeds as build_corpus; returns torch CUDA tensors:
+    dict(iq float64 [2 * total], lts1 int64 [n], avail int32 [n]) plus the numpy frame_off / lengths / rates."""
+    import torch
+
+    from . import rx as _rx
+    L = _rx.load_library()
+    fn = L.b200tx_build_batch_dev
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                   C.POINTER(Channel)]
+    n = len(payloads)
+    rates = np.ascontiguousarray(rates, dtype=np.uint8)
+    if isinstance(payloads, np.ndarray) and payloads.ndim == 2:
+        lengths = np.full(n, payloads.shape[1], dtype=np.uint32)
+        blob = np.ascontiguousarray(payloads, dtype=np.uint8).reshape(-1)
+        poff = (np.arange(n, dtype=np.uint64) * np.uint64(payloads.shape[1])).astype(np.uint64)
+    else:
+        lengths = np.array([len(p) for p in payloads], dtype=np.uint32)
+        poff = np.zeros(n, dtype=np.uint64)
+        poff[1:] = np.cumsum(lengths[:-1], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(bytes(p) for p in payloads) + b"\0", dtype=np.uint8)
+    if blob.size == 0:
+        blob = np.zeros(1, np.uint8)
+    ns = np.array([frame_samples(int(r), int(l)) for r, l in zip(rates, lengths)], dtype=np.uint64)
+    span = ns + np.uint64(lead_in)
+    off = np.zeros(n, dtype=np.uint64)
+    off[1:] = np.cumsum(span[:-1], dtype=np.uint64)
+    total = int(span.sum())
+    dev = torch.device("cuda", device)
+    d_blob = torch.from_numpy(blob.copy()).to(dev)
+    d_poff = torch.from_numpy(poff.astype(np.int64)).to(dev)
+    d_len = torch.from_numpy(lengths.astype(np.int32)).to(dev)
+    d_rates = torch.from_numpy(rates.copy()).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    iq = torch.empty(2 * total, dtype=torch.float64, device=dev)
+    ch = Channel(float(snr_db if snr_db is not None else 1000.0), int(multipath_taps), int(lead_in), int(seed), 0, 0)
+    s = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    rc = fn(device, C.c_void_p(s), d_blob.data_ptr(), d_poff.data_ptr(), d_len.data_ptr(), d_rates.data_ptr(), n,
+            iq.data_ptr(), d_off.data_ptr(), C.byref(ch))
+    if rc != 0:
+        raise B200RxError("b200tx_build_batch_dev failed (%d)" % rc)
+    torch.cuda.current_stream(dev).synchronize() if stream is None else None
+    lts1 = torch.from_numpy((off + np.uint64(lead_in + LTS1_OFFSET)).astype(np.int64)).to(dev)
+    avail = torch.from_numpy((ns - np.uint64(LTS1_OFFSET)).astype(np.int32)).to(dev)
+    return dict(iq=iq, lts1=lts1, avail=avail, frame_off=off, lengths=lengths, rates=rates, keep=(d_blob, d_poff, d_len, d_rates, d_off))

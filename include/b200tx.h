@@ -61,6 +61,21 @@ B200TX_API int b200tx_build_batch(const uint8_t *payloads, const uint64_t *paylo
                                   const uint8_t *rates, uint32_t n_frames, double *iq_out, const uint64_t *out_off,
                                   const b200tx_channel *ch);
 
+/* The same generator on the GPU: every pointer except `ch` is a DEVICE pointer, the stream is written
+ * straight into HBM (fun_ofdm_b200/csrc/txgen.cu, exported by libb200rx.so - there is no host implementation behind
+ * this entry point).  Same layout, same seeds, same counter-based noise as b200tx_build_batch: coded bits are identical,
+ * samples agree to ~1e-15.  Asynchronous on `cuda_stream` (a cudaStream_t, may be NULL); ch->n_threads is ignored.
+ * Returns 0, -1 (bad argument) or -2 (CUDA error). */
+#if defined(__GNUC__)
+#define B200TX_DEV_API __attribute__((visibility("default")))
+#else
+#define B200TX_DEV_API
+#endif
+B200TX_DEV_API int b200tx_build_batch_dev(int device, void *cuda_stream, const uint8_t *payloads_dev,
+                                          const uint64_t *payload_off_dev, const uint32_t *lengths_dev,
+                                          const uint8_t *rates_dev, uint32_t n_frames, double *iq_out_dev,
+                                          const uint64_t *out_off_dev, const b200tx_channel *ch);
+
 #ifdef __cplusplus
 }
 #endif
