@@ -96,8 +96,8 @@ __host__ __device__ __forceinline__ uint32_t branch_class(uint32_t j)
 }
 
 // ---- sample formats of the ingest side (b200rx_set_sample_format) ----
-// FC64 is the reference's own std::complex<double> (tagged_vector.h:82-94, usrp.cpp:43 cpu format "fc64"); FC32 and SC16
-// are the narrower formats the same samples have on the radio side (usrp.cpp:44 wire format "sc16").  The widening to
+// FC64 is the reference's own std::complex<double> (tagged_vector.h:82-94, usrp.cpp:43-44 cpu format "fc64"); FC32 and SC16
+// are the narrower formats the same samples have before UHD widens them on the host.  The widening to
 // double happens in the load, exactly (float -> double) or with one rounding ((double)int16 * scale), so the kernels
 // compute what the reference computes when it is handed the widened samples.
 enum { FMT_FC64 = B200RX_FMT_FC64, FMT_FC32 = B200RX_FMT_FC32, FMT_SC16 = B200RX_FMT_SC16 };

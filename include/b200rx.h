@@ -107,9 +107,10 @@ B200RX_API int b200rx_set_stream(b200rx_handle *h, void *cuda_stream);
 B200RX_API int b200rx_synchronize(b200rx_handle *h);
 
 /* ---- sample format of every `iq` argument (wire-format ingestion) ----
- * FC64 (default) is the reference's own std::complex<double> (tagged_vector.h:82-94; usrp.cpp:43 asks UHD for "fc64").
- * FC32 and SC16 are what the same samples are on the radio side (usrp.cpp:44: wire format "sc16"): taking them as they
- * are halves / quarters the bytes that cross PCIe, which is what bounds the host-buffer entry points.  Samples are
+ * FC64 (default) is the reference's own std::complex<double> (tagged_vector.h:82-94; usrp.cpp:43-44 asks UHD for the cpu
+ * format "fc64", i.e. UHD widens its 16-bit over-the-wire samples on the host).  FC32 and SC16 are what the same samples
+ * are before that widening: taking them as they are halves / quarters the bytes that cross PCIe, which is what bounds
+ * the host-buffer entry points.  Samples are
  * widened to double in the kernels' loads - (double)float exactly, (double)int16 * sc16_scale with one rounding - and
  * everything after that is the same fp64 arithmetic, so results are bit-identical to the reference fed the widened
  * samples.  Applies to all later calls on the handle; `iq` pointers are then float[2] / int16_t[2] per sample. */
