@@ -128,3 +128,26 @@ def test_corpus_is_deterministic_and_decodes_with_the_port(built, port):
         d = port.decode_frame(m["iq"][off: off + n])
         ok += int(d.hdr_ok and d.crc_ok)
     assert ok >= 2
+
+
+def test_block_adapter_compiles_against_the_reference_headers(tmp_path):
+    """b200_rx.cpp built with -DB200_USE_REFERENCE_HEADERS uses the reference's own block.h /
+    tagged_vector.h (not this repo's mirror in fun_api.h), i.e. the adapter really is a fun::block of the reference."""
+    import shutil
+    import subprocess
+    ref_src = "/root/reference/src"
+    if not os.path.isdir(ref_src):
+        pytest.skip("reference sources not present on this box")
+    cxx = shutil.which("g++") or "/opt/gcc/bin/g++"
+    host = os.path.join(ROOT, "fun_ofdm_b200", "host")
+    for src in ("b200_rx.cpp", "b200_receiver_chain.cpp"):
+        obj = tmp_path / (src + ".o")
+        cmd = [cxx, "-std=c++11", "-O1", "-fPIC", "-c", "-DB200_USE_REFERENCE_HEADERS", "-I", ref_src, "-I", host,
+               os.path.join(host, src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert obj.stat().st_size > 0
+    # the mirror header and the reference agree on what the adapter relies on
+    text = open(os.path.join(ref_src, "tagged_vector.h")).read()
+    for name in ("NONE", "STS_START", "STS_END", "LTS_START", "LTS1", "LTS2", "START_OF_FRAME"):
+        assert name in text
