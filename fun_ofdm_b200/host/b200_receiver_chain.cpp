@@ -21,6 +21,7 @@ namespace fun
         m_handle(nullptr),
         m_max_frames(max_frames ? max_frames : 1),
         m_max_payload(max_payload > 4095 ? 4095 : (max_payload ? max_payload : 1)),
+        m_buf(nullptr), m_buf_n(0), m_buf_cap(0),
         m_base(0), m_handled(0), m_last_lts1(-1), m_pending_lts1(-1), m_phase(0.0)
     {
         std::memset(&m_counters, 0, sizeof(m_counters));
@@ -45,29 +46,55 @@ namespace fun
     b200_receiver_chain::~b200_receiver_chain()
     {
         if (m_handle) b200rx_destroy(m_handle);
+        if (m_buf) b200rx_host_free(m_buf);
+    }
+
+    bool b200_receiver_chain::reserve(size_t n)
+    {
+        if (n <= m_buf_cap) return true;
+        size_t cap = m_buf_cap ? m_buf_cap : 65536;
+        while (cap < n) cap *= 2;
+        void *p = nullptr;
+        if (b200rx_host_alloc(&p, cap * sizeof(std::complex<double>)) != B200RX_OK) return false;
+        if (m_buf_n) std::memcpy(p, static_cast<const void *>(m_buf), m_buf_n * sizeof(std::complex<double>));
+        if (m_buf) b200rx_host_free(m_buf);
+        m_buf = static_cast<std::complex<double> *>(p);
+        m_buf_cap = cap;
+        return true;
     }
 
     std::vector<std::vector<unsigned char> > b200_receiver_chain::process_samples(std::vector<std::complex<double> > samples)
     {
+        return process_samples(samples.data(), samples.size());
+    }
+
+    std::vector<std::vector<unsigned char> > b200_receiver_chain::process_samples(const std::complex<double> *samples, size_t n)
+    {
         std::vector<std::vector<unsigned char> > out;
         if (!m_handle) return out;
         m_counters.calls++;
-        m_counters.samples += samples.size();
+        m_counters.samples += n;
         size_t fed = 0;
         do { // one GPU pass per MAX_CAPTURE new samples (normally one pass per call)
-            const size_t take = samples.size() - fed < MAX_CAPTURE ? samples.size() - fed : (size_t)MAX_CAPTURE;
-            m_buf.insert(m_buf.end(), samples.begin() + fed, samples.begin() + fed + take);
+            const size_t take = n - fed < MAX_CAPTURE ? n - fed : (size_t)MAX_CAPTURE;
+            if (!reserve(m_buf_n + take)) {
+                std::cerr << "b200_receiver_chain: out of pinned host memory" << std::endl;
+                return out;
+            }
+            if (take) std::memcpy(static_cast<void *>(m_buf + m_buf_n), static_cast<const void *>(samples + fed),
+                                  take * sizeof(std::complex<double>));
+            m_buf_n += take;
             fed += take;
             run_capture(out);
-        } while (fed < samples.size());
+        } while (fed < n);
         return out;
     }
 
     std::vector<std::vector<unsigned char> > b200_receiver_chain::flush(unsigned pad)
     {
         std::vector<std::vector<unsigned char> > out = process_samples(std::vector<std::complex<double> >(pad));
-        m_base += m_buf.size();
-        m_buf.clear();
+        m_base += m_buf_n;
+        m_buf_n = 0;
         m_handled = m_base;
         m_pending_lts1 = -1;
         return out;
@@ -75,16 +102,16 @@ namespace fun
 
     void b200_receiver_chain::run_capture(std::vector<std::vector<unsigned char> > &out)
     {
-        const uint64_t n = m_buf.size();
+        const uint64_t n = m_buf_n;
         if (n == 0) return;
         b200rx_sync_result res;
         std::memset(&res, 0, sizeof(res));
-        int rc = b200rx_receive(m_handle, reinterpret_cast<const double *>(m_buf.data()), n, m_phase, m_payload.data(),
+        int rc = b200rx_receive(m_handle, m_buf, n, m_phase, m_payload.data(),
                                 m_max_payload, m_len.data(), m_rate.data(), m_status.data(), m_lts1.data(), &res);
         if (rc != B200RX_OK) {
             std::cerr << "b200_receiver_chain: " << b200rx_last_error(m_handle) << std::endl;
             m_base += n;
-            m_buf.clear();
+            m_buf_n = 0;
             m_handled = m_base;
             return;
         }
@@ -137,7 +164,10 @@ namespace fun
             // m_phase_acc in front of the new buffer: the last synchronised frame's (it either lies in the dropped part,
             // or it is recomputed from the retained samples and this value is not used)
             if (res.phase_valid) m_phase = res.last_phase;
-            m_buf.erase(m_buf.begin(), m_buf.begin() + (size_t)(keep_from - m_base));
+            const size_t drop = (size_t)(keep_from - m_base);
+            m_buf_n -= drop;
+            if (m_buf_n) std::memmove(static_cast<void *>(m_buf), static_cast<const void *>(m_buf + drop),
+                                      m_buf_n * sizeof(std::complex<double>));
             m_base = keep_from;
         }
     }

@@ -38,6 +38,8 @@ namespace fun
         ~b200_receiver_chain();
 
         std::vector<std::vector<unsigned char> > process_samples(std::vector<std::complex<double> > samples);
+        // same, without the by-value vector (one host copy less per call)
+        std::vector<std::vector<unsigned char> > process_samples(const std::complex<double> *samples, size_t n);
 
         // End of stream: pushes `pad` zero samples through (the reference needs trailing samples just the same:
         // test_sim.cpp:75-77 pads its stream with zeros) and drops whatever is still incomplete.
@@ -54,7 +56,11 @@ namespace fun
         b200rx_handle *m_handle;
         std::string m_error;
         unsigned m_max_frames, m_max_payload;
-        std::vector<std::complex<double> > m_buf; // retained tail of the stream + the new samples
+        // retained tail of the stream + the new samples, in pinned host memory (the H2D copy of a pageable std::vector
+        // would be staged by the driver at a fraction of the link rate)
+        std::complex<double> *m_buf;
+        size_t m_buf_n, m_buf_cap;
+        bool reserve(size_t n);
         uint64_t m_base;                           // stream index of m_buf[0]
         uint64_t m_handled;                        // STS_END tags below this stream index have been examined
         int64_t m_last_lts1;                       // LTS1 index of the last frame delivered or dropped for good (-1: none)

@@ -68,8 +68,7 @@ API int b200host_chain_process(void *chain, const double *iq, long n, uint8_t *p
     std::vector<std::vector<unsigned char> > out;
     if (n < 0) out = c->flush();
     else {
-        const std::complex<double> *p = reinterpret_cast<const std::complex<double> *>(iq);
-        out = c->process_samples(std::vector<std::complex<double> >(p, p + n));
+        out = c->process_samples(reinterpret_cast<const std::complex<double> *>(iq), (size_t)n);
     }
     int count = 0;
     for (size_t k = 0; k < out.size(); k++, count++) {
