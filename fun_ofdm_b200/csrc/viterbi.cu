@@ -52,7 +52,7 @@ __global__ void bm_from_symbols_kernel(const uint8_t *symbols, uint64_t symbols_
 // Per 24 steps and frame: one 96 B read of metric words (staged through shared memory, double
 // buffered, prefetched one block ahead) and three 64 B survivor stores.
 // ------------------------------------------------------------------------------------------------
-template <int LB>
+template <int LB, int RN>
 __global__ void __launch_bounds__(64) viterbi_acs2_kernel(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride,
                                                           uint32_t *dec, uint32_t dec_stride_words, uint32_t n_frames,
                                                           uint32_t neg1)
@@ -117,20 +117,20 @@ __global__ void __launch_bounds__(64) viterbi_acs2_kernel(const FrameDesc *desc,
             for (int j = 0; j < NR / 2; j++) acc[j] = 0;
             // 8 steps; phase = (8 * o + i) % 6
             if (o == 0) {
-                A::template one<0>(R, acc, wa.x, L, glane, group); A::template one<1>(R, acc, wa.y, L, glane, group);
-                A::template one<2>(R, acc, wa.z, L, glane, group); A::template one<3>(R, acc, wa.w, L, glane, group);
-                A::template one<4>(R, acc, wb.x, L, glane, group); A::template one<5>(R, acc, wb.y, L, glane, group);
-                A::template one<0>(R, acc, wb.z, L, glane, group); A::template one<1>(R, acc, wb.w, L, glane, group);
+                A::template one<0, RN>(R, acc, wa.x, L, glane, group); A::template one<1, RN>(R, acc, wa.y, L, glane, group);
+                A::template one<2, RN>(R, acc, wa.z, L, glane, group); A::template one<3, RN>(R, acc, wa.w, L, glane, group);
+                A::template one<4, RN>(R, acc, wb.x, L, glane, group); A::template one<5, RN>(R, acc, wb.y, L, glane, group);
+                A::template one<0, RN>(R, acc, wb.z, L, glane, group); A::template one<1, RN>(R, acc, wb.w, L, glane, group);
             } else if (o == 1) {
-                A::template one<2>(R, acc, wa.x, L, glane, group); A::template one<3>(R, acc, wa.y, L, glane, group);
-                A::template one<4>(R, acc, wa.z, L, glane, group); A::template one<5>(R, acc, wa.w, L, glane, group);
-                A::template one<0>(R, acc, wb.x, L, glane, group); A::template one<1>(R, acc, wb.y, L, glane, group);
-                A::template one<2>(R, acc, wb.z, L, glane, group); A::template one<3>(R, acc, wb.w, L, glane, group);
+                A::template one<2, RN>(R, acc, wa.x, L, glane, group); A::template one<3, RN>(R, acc, wa.y, L, glane, group);
+                A::template one<4, RN>(R, acc, wa.z, L, glane, group); A::template one<5, RN>(R, acc, wa.w, L, glane, group);
+                A::template one<0, RN>(R, acc, wb.x, L, glane, group); A::template one<1, RN>(R, acc, wb.y, L, glane, group);
+                A::template one<2, RN>(R, acc, wb.z, L, glane, group); A::template one<3, RN>(R, acc, wb.w, L, glane, group);
             } else {
-                A::template one<4>(R, acc, wa.x, L, glane, group); A::template one<5>(R, acc, wa.y, L, glane, group);
-                A::template one<0>(R, acc, wa.z, L, glane, group); A::template one<1>(R, acc, wa.w, L, glane, group);
-                A::template one<2>(R, acc, wb.x, L, glane, group); A::template one<3>(R, acc, wb.y, L, glane, group);
-                A::template one<4>(R, acc, wb.z, L, glane, group); A::template one<5>(R, acc, wb.w, L, glane, group);
+                A::template one<4, RN>(R, acc, wa.x, L, glane, group); A::template one<5, RN>(R, acc, wa.y, L, glane, group);
+                A::template one<0, RN>(R, acc, wa.z, L, glane, group); A::template one<1, RN>(R, acc, wa.w, L, glane, group);
+                A::template one<2, RN>(R, acc, wb.x, L, glane, group); A::template one<3, RN>(R, acc, wb.y, L, glane, group);
+                A::template one<4, RN>(R, acc, wb.z, L, glane, group); A::template one<5, RN>(R, acc, wb.w, L, glane, group);
             }
             if (store) {
                 uint32_t *dst = d_blk + o * ACS2_WORDS_PER_8;
@@ -480,9 +480,19 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
     if (forced >= 2 && forced <= 4) lb = forced;
     const uint32_t per_cta = 2u * (32u >> lb);
     const uint32_t grid = (n_frames + per_cta - 1) / per_cta;
-    if (lb == 2) viterbi_acs2_kernel<2><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu);
-    else if (lb == 3) viterbi_acs2_kernel<3><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu);
-    else viterbi_acs2_kernel<4><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu);
+    static int rn = -1; // renormalisation variant (viterbi_acs2.cuh group_min), B200RX_ACS_RN for experiments
+    if (rn < 0) {
+        const char *e = getenv("B200RX_ACS_RN");
+        rn = e ? atoi(e) : ACS2_DEFAULT_RN;
+        if (rn < 0 || rn > 1) rn = ACS2_DEFAULT_RN;
+    }
+#define ACS2_LAUNCH(LBV, RNV) viterbi_acs2_kernel<LBV, RNV><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu)
+#define ACS2_LAUNCH_RN(LBV) do { if (rn == 0) ACS2_LAUNCH(LBV, 0); else ACS2_LAUNCH(LBV, 1); } while (0)
+    if (lb == 2) ACS2_LAUNCH_RN(2);
+    else if (lb == 3) ACS2_LAUNCH_RN(3);
+    else ACS2_LAUNCH_RN(4);
+#undef ACS2_LAUNCH_RN
+#undef ACS2_LAUNCH
     return cudaGetLastError();
 }
 
