@@ -49,16 +49,15 @@ __device__ __forceinline__ int shifted_index(int lane, int slot) { return ((slot
 template <int NBITS>
 __device__ __forceinline__ void qam_decode_axis(double x, double scale, uint8_t *bits)
 {
-    int pt = __double2int_rz(x * scale);
-    int flip = 1;
+    // qam.h:112-122 is: bit_i = clamp(flip * pt + 128); b = pt < 0 ? -1 : 1; pt -= b * amp; flip = -b; amp /= 2.
+    // With u_0 = pt the quantity flip * pt obeys u_{i+1} = amp_i - |u_i| (pt - b * amp = b * (|pt| - amp), times -b),
+    // so each further soft bit is one abs, one subtract and one clamp.
+    int u = __double2int_rz(x * scale);
     int amp = (1 << (NBITS - 1)) << (8 - NBITS);
 #pragma unroll
     for (int i = 0; i < NBITS; i++) {
-        int v = flip * pt + 128;
-        bits[i] = (uint8_t)min(max(v, 0), 255);
-        const int sgn = pt < 0 ? -1 : 1;
-        pt -= sgn * amp;
-        flip = -sgn;
+        bits[i] = (uint8_t)min(max(u + 128, 0), 255);
+        u = amp - abs(u);
         amp >>= 1;
     }
 }
@@ -158,7 +157,7 @@ struct SymbolCtx {
 
 // One OFDM symbol: samples -> equalised, derotated data carriers -> soft bits in ctx.soft.
 // v = symbol index from SIGNAL (0) on: selects the pilot polarity (phase_tracker.cpp:77-86).
-template <bool ROT, int FMT>
+template <bool ROT, int FMT, bool DBG>
 __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const Window &win, int off, const RotCtx &rc, int v,
                                                int bpsc, int lane, double2 *dbg_eq)
 {
@@ -168,16 +167,17 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const Windo
     ctx.xs[shifted_index(lane, 1)] = v1;
     __syncwarp();
 
-    // phase_tracker.cpp:83-92: e = sum_p rec_p * conj(ref_p) / 4, ref_p = sign_p * POLARITY[v % 127] (real)
+    // phase_tracker.cpp:83-92: e = sum_p rec_p * conj(ref_p) / 4, ref_p = sign_p * POLARITY[v % 127] (real).
+    // Lane l takes pilot l & 3; two butterfly additions give every lane the sum of the four terms.
     const double pol = (double)c_polarity[v % 127];
-    double2 e = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const int bin = 11 + 14 * p;
+    double2 e;
+    {
+        const int p = lane & 3, bin = 11 + 14 * p;
         const double ref = (p == 3) ? -pol : pol;
         const double2 rec = cmul(ctx.hinv[bin], ctx.xs[bin]);
-        e.x += rec.x * ref / 4.0;
-        e.y += rec.y * ref / 4.0;
+        e = make_double2(rec.x * ref / 4.0, rec.y * ref / 4.0);
+        e = cadd(e, shfl_xor2(e, 1));
+        e = cadd(e, shfl_xor2(e, 2));
     }
     // phase_tracker.cpp:92-98 rotates by exp(-i arg(e)) = conj(e) / |e|
     const double m2 = e.x * e.x + e.y * e.y;
@@ -191,7 +191,7 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const Windo
         if (c < 48) {
             const int bin = data_bin(c);
             const double2 y = cmul(cmul(ctx.hinv[bin], ctx.xs[bin]), rot);
-            if (dbg_eq) dbg_eq[c] = y;
+            if constexpr (DBG) { if (dbg_eq) dbg_eq[c] = y; }
             uint8_t *o = ctx.soft + c * bpsc;
             switch (bpsc) { // modulator.cpp:118-160: real axis first, then imaginary
                 case 1: qam_decode_axis<1>(y.x, scale, o); break;
@@ -204,7 +204,8 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const Windo
     __syncwarp();
 }
 
-template <bool ROT, int FMT>
+// DBG: the parity-test taps (equalised points, depunctured soft symbols) are compiled in only for calls that ask for them
+template <bool ROT, int FMT, bool DBG>
 __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 {
     __shared__ double2 s_tw[64];
@@ -276,8 +277,9 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
 
     // ---- SIGNAL: ppdu.cpp:168-218 ----
     if (warp == 0) {
-        double2 *dbg = a.dbg_eq ? a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors) * 48 : nullptr;
-        process_symbol<ROT, FMT>(ctx, win, 128 + 16, rc, 0, 1, lane, (dbg && a.dbg_eq_vectors > 0) ? dbg : nullptr);
+        double2 *dbg = nullptr;
+        if constexpr (DBG) { if (a.dbg_eq && a.dbg_eq_vectors > 0) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors) * 48; }
+        process_symbol<ROT, FMT, DBG>(ctx, win, 128 + 16, rc, 0, 1, lane, dbg);
         if (lane < 24) {
             uint32_t s0, s1;
             step_symbols(ctx.soft, PUNC_1_2, lane, s0, s1);
@@ -323,17 +325,19 @@ __global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
     uint32_t *bm_out = a.bm + (size_t)frame * a.bm_stride;
     for (uint32_t s = warp; s < nsym; s += FE_WARPS) {
         double2 *dbg = nullptr;
-        if (a.dbg_eq && s + 1 < a.dbg_eq_vectors) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors + s + 1) * 48;
-        process_symbol<ROT, FMT>(ctx, win, 128 + 80 * (int)(s + 1) + 16, rc, (int)(s + 1), rr.bpsc, lane, dbg);
+        if constexpr (DBG) { if (a.dbg_eq && s + 1 < a.dbg_eq_vectors) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors + s + 1) * 48; }
+        process_symbol<ROT, FMT, DBG>(ctx, win, 128 + 80 * (int)(s + 1) + 16, rc, (int)(s + 1), rr.bpsc, lane, dbg);
         uint32_t *sym_out = bm_out + (size_t)s * rr.dbps;
         for (int t = lane; t < rr.dbps; t += 32) {
             const uint32_t pair = s_idx[t];
             const uint32_t s0 = ctx.soft[pair & 0xFFFFu], s1 = ctx.soft[pair >> 16];
             const size_t step = (size_t)s * rr.dbps + t;
             sym_out[t] = bm_word(s0, s1);
-            if (a.dbg_depunct && 2 * step + 1 < a.dbg_depunct_stride) {
-                uint8_t *dp = a.dbg_depunct + (size_t)frame * a.dbg_depunct_stride + 2 * step;
-                dp[0] = (uint8_t)s0; dp[1] = (uint8_t)s1;
+            if constexpr (DBG) {
+                if (a.dbg_depunct && 2 * step + 1 < a.dbg_depunct_stride) {
+                    uint8_t *dp = a.dbg_depunct + (size_t)frame * a.dbg_depunct_stride + 2 * step;
+                    dp[0] = (uint8_t)s0; dp[1] = (uint8_t)s1;
+                }
             }
         }
         __syncwarp();
@@ -360,15 +364,19 @@ cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s)
 {
     if (a.n_frames == 0) return cudaSuccess;
     const dim3 grid(a.n_frames), block(FE_WARPS * 32);
+    const bool dbg = a.dbg_eq != nullptr || a.dbg_depunct != nullptr;
+#define FE_LAUNCH(ROTV, FMTV) do { if (dbg) frontend_kernel<ROTV, FMTV, true><<<grid, block, 0, s>>>(a); \
+                                   else frontend_kernel<ROTV, FMTV, false><<<grid, block, 0, s>>>(a); } while (0)
     switch (a.fmt * 2 + (a.rot ? 1 : 0)) {
-        case FMT_FC64 * 2: frontend_kernel<false, FMT_FC64><<<grid, block, 0, s>>>(a); break;
-        case FMT_FC64 * 2 + 1: frontend_kernel<true, FMT_FC64><<<grid, block, 0, s>>>(a); break;
-        case FMT_FC32 * 2: frontend_kernel<false, FMT_FC32><<<grid, block, 0, s>>>(a); break;
-        case FMT_FC32 * 2 + 1: frontend_kernel<true, FMT_FC32><<<grid, block, 0, s>>>(a); break;
-        case FMT_SC16 * 2: frontend_kernel<false, FMT_SC16><<<grid, block, 0, s>>>(a); break;
-        case FMT_SC16 * 2 + 1: frontend_kernel<true, FMT_SC16><<<grid, block, 0, s>>>(a); break;
+        case FMT_FC64 * 2: FE_LAUNCH(false, FMT_FC64); break;
+        case FMT_FC64 * 2 + 1: FE_LAUNCH(true, FMT_FC64); break;
+        case FMT_FC32 * 2: FE_LAUNCH(false, FMT_FC32); break;
+        case FMT_FC32 * 2 + 1: FE_LAUNCH(true, FMT_FC32); break;
+        case FMT_SC16 * 2: FE_LAUNCH(false, FMT_SC16); break;
+        case FMT_SC16 * 2 + 1: FE_LAUNCH(true, FMT_SC16); break;
         default: return cudaErrorInvalidValue;
     }
+#undef FE_LAUNCH
     return cudaGetLastError();
 }
 

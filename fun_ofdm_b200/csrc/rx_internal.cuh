@@ -78,12 +78,24 @@ struct FrameDesc {
 // the four distinct values pavgb/psrlw produce in viterbi.cpp:234-248 (Branchtab entries are 0 or 255).
 __host__ __device__ __forceinline__ uint32_t bm_word(uint32_t s0, uint32_t s1)
 {
+#ifdef __CUDA_ARCH__
+    // the same four values from two sums: with a = s0 + s1 + 1 and d = s0 - s1 + 256 (both 1..511),
+    // m00 = a >> 3, m01 = d >> 3, m10 = (512 - d) >> 3, m11 = (512 - a) >> 3   (255 - s = s ^ 255)
+    const uint32_t a = s0 + s1 + 1u;
+    const uint32_t d = s0 - s1 + 256u;
+    const uint32_t P = d * 65536u + a;
+    const uint32_t Q = 0x02000200u - P;
+    const uint32_t A = (P >> 3) & 0x003F003Fu; // m00 | m01 << 16
+    const uint32_t B = (Q >> 3) & 0x003F003Fu; // m11 | m10 << 16
+    return __byte_perm(A, B, 0x4620u);         // m00 | m01 << 8 | m10 << 16 | m11 << 24
+#else
     const uint32_t n0 = s0 ^ 255u, n1 = s1 ^ 255u;
     const uint32_t m00 = (s0 + s1 + 1u) >> 3;
     const uint32_t m01 = (s0 + n1 + 1u) >> 3;
     const uint32_t m10 = (n0 + s1 + 1u) >> 3;
     const uint32_t m11 = (n0 + n1 + 1u) >> 3;
     return m00 | (m01 << 8) | (m10 << 16) | (m11 << 24);
+#endif
 }
 
 // Branch class of butterfly j (0..31): Branchtab[0][j] = parity(2j & 121), Branchtab[1][j] = parity(2j & 91)
