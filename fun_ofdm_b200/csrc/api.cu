@@ -83,6 +83,11 @@ struct b200rx_handle {
     uint32_t sy_ev_cap = 0;
     SyncSummary *sy_summary_host = nullptr; // pinned
 
+    // work() buffer origins for the next raw-capture call (b200rx_set_receive_origins); device copy per sync lane
+    std::vector<int64_t> origins;
+    int64_t *d_origins[B200RX_MAX_PIPELINE_DEPTH] = {};
+    uint32_t d_origins_cap[B200RX_MAX_PIPELINE_DEPTH] = {};
+
     // format of every `iq` argument (b200rx_set_sample_format)
     int fmt = FMT_FC64;
     double scale = 1.0;
@@ -301,6 +306,7 @@ int b200rx_destroy(b200rx_handle *h)
         cudaFree(y.ev_x); cudaFree(y.ev_count); cudaFree(y.rec); cudaFree(y.cta_ev); cudaFree(y.cta_cnt); cudaFree(y.lts1);
         cudaFree(y.avail); cudaFree(y.rot); cudaFree(y.phase); cudaFree(y.summary);
     }
+    for (auto p : h->d_origins) cudaFree(p);
     if (h->sy_summary_host) cudaFreeHost(h->sy_summary_host);
     use_lane(h, 0);
     cudaFree(h->desc); cudaFree(h->bm); cudaFree(h->dec); cudaFree(h->counters);
@@ -339,6 +345,15 @@ int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale)
     if (format == B200RX_FMT_SC16 && !(sc16_scale > 0.0)) return fail(h, B200RX_E_ARG, "b200rx_set_sample_format: scale must be > 0");
     h->fmt = format;
     h->scale = format == B200RX_FMT_SC16 ? sc16_scale : 1.0;
+    return B200RX_OK;
+}
+
+int b200rx_set_receive_origins(b200rx_handle *h, const int64_t *origins, uint32_t n)
+{
+    if (!h || (n && !origins)) return B200RX_E_ARG;
+    for (uint32_t i = 1; i < n; i++)
+        if (origins[i] < origins[i - 1]) return fail(h, B200RX_E_ARG, "b200rx_set_receive_origins: origins must ascend");
+    h->origins.assign(origins, origins + n);
     return B200RX_OK;
 }
 
@@ -791,6 +806,20 @@ int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const void *iq_
     a.tags = tags_dev;
     a.ev_x = y.ev_x; a.ev_count = y.ev_count; a.ev_cap = h->sy_ev_cap;
     a.rec = y.rec; a.cta_ev = y.cta_ev; a.cta_cnt = y.cta_cnt;
+    if (!h->origins.empty()) { // consumed by this call
+        const uint32_t no = (uint32_t)h->origins.size();
+        if (no > h->d_origins_cap[lane]) {
+            if (h->d_origins[lane]) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_origins[lane]); h->d_origins[lane] = nullptr; }
+            cudaError_t e = cudaMalloc((void **)&h->d_origins[lane], (size_t)no * 2 * sizeof(int64_t));
+            if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "sync scratch (buffer origins)", e);
+            h->d_origins_cap[lane] = no * 2;
+        }
+        // pageable source: the copy is staged before the call returns, the vector may be reused right away
+        CU(h, cudaMemcpyAsync(h->d_origins[lane], h->origins.data(), no * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        a.origins = h->d_origins[lane];
+        a.n_origins = no;
+        h->origins.clear();
+    }
     a.lts1 = y.lts1; a.avail = y.avail; a.rot = y.rot; a.phase = y.phase;
     a.summary = y.summary;
     CU(h, launch_sync(a, s));

@@ -168,6 +168,8 @@ struct SyncArgs {
     uint64_t *ev_x;       // scratch [ev_cap]: STS_END positions in stream order
     uint32_t *ev_count;   // scratch [2]: events kept, events lost
     uint32_t ev_cap;
+    const int64_t *origins; // device, ascending: work() buffer origins of a chunked stream (null: one buffer at -160)
+    uint32_t n_origins;
     SyncRec *rec;         // scratch [ev_cap]
     uint64_t *lts1;       // [max_frames]
     uint32_t *avail;      // [max_frames]

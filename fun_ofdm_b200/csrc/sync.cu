@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_events_kernel(const CtaEven
 // (timing_sync.cpp:89-118) on one thread.
 template <int FMT>
 __global__ void __launch_bounds__(128) lts_sync_kernel(const void *iq, double scale, uint64_t n, const uint64_t *ev_x,
-                                                       const uint32_t *ev_count, uint32_t ev_cap, SyncRec *rec)
+                                                       const uint32_t *ev_count, uint32_t ev_cap, SyncRec *rec,
+                                                       const int64_t *origins, uint32_t n_origins)
 {
     __shared__ double2 s_s[160];
     __shared__ double s_val[96];
@@ -274,8 +275,17 @@ __global__ void __launch_bounds__(128) lts_sync_kernel(const void *iq, double sc
                 const int d = bp[0] - bp[t];
                 if (d == 64 || d == -64) {
                     const int first = bp[0] < bp[t] ? bp[0] : bp[t];
-                    const int lts_offset = first - 32; // relative to x; never below the stream start for x >= 32
-                    if ((int64_t)x + lts_offset >= -160) {
+                    const int lts_offset = first - 32; // relative to x
+                    // timing_sync.cpp:102 `if(lts_offset < 0) break;` is evaluated in the coordinates of the work() buffer
+                    // that examines the tag: 160 carried-over samples in front of the caller's chunk.  One capture = one
+                    // buffer starting 160 samples before the capture; a caller that reproduces a chunked stream passes
+                    // the buffer origins of its chunks (b200rx_set_receive_origins), the last one <= x applies.
+                    int64_t origin = -160;
+                    for (uint32_t o = 0; o < n_origins; o++) {
+                        const int64_t v = origins[o];
+                        if (v <= (int64_t)x) origin = v; else break;
+                    }
+                    if ((int64_t)x + lts_offset >= origin) {
                         r.found = 1;
                         r.lts1 = (int64_t)x + lts_offset + 24;
                         // m_phase_acc = arg(input[lts_offset + 32 + 2 * 64 - 1] * LTS_TIME_DOMAIN_CONJ[63])
@@ -439,9 +449,9 @@ cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s)
         // enough CTAs for one event each at the usual rates; the kernel strides over the rest
         const unsigned lts_grid = a.ev_cap < 4096u ? a.ev_cap : 4096u;
         switch (a.fmt) {
-            case FMT_FC64: lts_sync_kernel<FMT_FC64><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec); break;
-            case FMT_FC32: lts_sync_kernel<FMT_FC32><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec); break;
-            default: lts_sync_kernel<FMT_SC16><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec); break;
+            case FMT_FC64: lts_sync_kernel<FMT_FC64><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins); break;
+            case FMT_FC32: lts_sync_kernel<FMT_FC32><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins); break;
+            default: lts_sync_kernel<FMT_SC16><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins); break;
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

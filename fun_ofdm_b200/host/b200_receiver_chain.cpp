@@ -74,6 +74,7 @@ namespace fun
         if (!m_handle) return out;
         m_counters.calls++;
         m_counters.samples += n;
+        m_calls.push_back(m_base + m_buf_n);
         size_t fed = 0;
         do { // one GPU pass per MAX_CAPTURE new samples (normally one pass per call)
             const size_t take = n - fed < MAX_CAPTURE ? n - fed : (size_t)MAX_CAPTURE;
@@ -104,6 +105,12 @@ namespace fun
     {
         const uint64_t n = m_buf_n;
         if (n == 0) return;
+        // origins of the reference's work() buffers inside the retained samples: chunk start - 160, relative to m_buf[0];
+        // the last one at or before the buffer start and every later one
+        while (m_calls.size() > 1 && (int64_t)m_calls[1] - 160 <= (int64_t)m_base) m_calls.pop_front();
+        std::vector<int64_t> origins(m_calls.size());
+        for (size_t i = 0; i < m_calls.size(); i++) origins[i] = (int64_t)m_calls[i] - 160 - (int64_t)m_base;
+        b200rx_set_receive_origins(m_handle, origins.data(), (uint32_t)origins.size());
         b200rx_sync_result res;
         std::memset(&res, 0, sizeof(res));
         int rc = b200rx_receive(m_handle, m_buf, n, m_phase, m_payload.data(),

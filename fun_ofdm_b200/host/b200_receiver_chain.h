@@ -14,7 +14,10 @@
 //     everything from 224 samples before the LTS1 tag of a frame whose samples have not all arrived yet;
 //   * m_phase_acc of the last synchronised frame;
 //   * the stream position below which frames have already been delivered (re-examined frames are recognised by the
-//     absolute index of their LTS1 tag).
+//     absolute index of their LTS1 tag);
+//   * where the caller cut the stream: the reference's timing_sync discards an LTS that starts before the 160 samples it
+//     carried over into the current work() buffer (timing_sync.cpp:102), so its output depends on the chunking; the
+//     boundaries are handed to the GPU pass (b200rx_set_receive_origins) and the same frames are dropped.
 // A frame is delivered in the call that brings its last sample; the reference delivers it up to five calls later
 // (one per block still in front of the payload).  Sequences of payloads are identical; per-call alignment is not.
 #ifndef B200_RECEIVER_CHAIN_H
@@ -22,6 +25,7 @@
 
 #include <complex>
 #include <cstdint>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -64,6 +68,7 @@ namespace fun
         uint64_t m_base;                           // stream index of m_buf[0]
         uint64_t m_handled;                        // STS_END tags below this stream index have been examined
         int64_t m_last_lts1;                       // LTS1 index of the last frame delivered or dropped for good (-1: none)
+        std::deque<uint64_t> m_calls;              // stream index at which each recent process_samples() call started
         int64_t m_pending_lts1;                    // LTS1 index of the frame still arriving (-1: none)
         double m_phase;                            // timing_sync's m_phase_acc in front of m_buf
         counters_t m_counters;

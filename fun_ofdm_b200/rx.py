@@ -114,6 +114,8 @@ def load_library():
     L.b200rx_decode_batch_dev.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp, C.POINTER(Debug)]
     L.b200rx_sync_dev.restype = C.c_int
     L.b200rx_sync_dev.argtypes = [vp, vp, u64, C.c_double, vp, vp, vp, vp, C.POINTER(SyncResult)]
+    L.b200rx_set_receive_origins.restype = C.c_int
+    L.b200rx_set_receive_origins.argtypes = [vp, vp, u32]
     L.b200rx_receive_dev.restype = C.c_int
     L.b200rx_receive_dev.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, vp, C.POINTER(SyncResult)]
     L.b200rx_receive.restype = C.c_int
@@ -327,6 +329,11 @@ class Receiver:
                                          C.byref(res) if wait else None)
         self._check(rc, "b200rx_receive_dev")
         return res.as_dict() if wait else None
+
+    def set_receive_origins(self, origins):
+        """Work()-buffer origins (chunk start - 160, relative to the next capture) of a chunked reference stream."""
+        o = np.ascontiguousarray(origins, dtype=np.int64)
+        self._check(self.lib.b200rx_set_receive_origins(self.h, o.ctypes.data, len(o)), "b200rx_set_receive_origins")
 
     def receive(self, samples, phase_in=0.0):
         """Host samples (complex128 array) -> (list of payload bytes of CRC-OK frames in stream order, info dict with

@@ -199,6 +199,15 @@ typedef struct b200rx_sync_result {
     uint32_t pad;
 } b200rx_sync_result;
 
+/* Chunked streams.  The reference's timing_sync::work() sees the caller's chunk behind 160 carried-over samples and
+ * discards an LTS whose start would lie before that buffer (timing_sync.cpp:102 `if(lts_offset < 0) break;`), so what
+ * it finds depends on where the caller cut the stream.  One capture is treated as one such buffer.  A caller that
+ * replays a chunked stream in larger captures (fun::b200_receiver_chain does) passes, before the call, the sample
+ * indices - relative to the capture, ascending, possibly negative - at which the reference's buffers would have started
+ * (chunk start - 160); the STS_END tag at x is then judged against the last origin <= x.  Consumed by the next
+ * b200rx_sync_dev / b200rx_receive / b200rx_receive_dev call. */
+B200RX_API int b200rx_set_receive_origins(b200rx_handle *h, const int64_t *origins, uint32_t n);
+
 /* Tags and frame list only.  tags_dev [n_samples] (nullable); lts1_index_dev / avail_dev [max_frames] as consumed by
  * b200rx_decode_batch_dev; phase_dev [max_frames] (nullable) the rotation phase of each frame.  phase_in is
  * m_phase_acc before the capture (0 for a fresh chain).  Synchronous: returns when `res` (host) is filled. */

@@ -114,3 +114,33 @@ def test_one_long_call_equals_many_short_ones(ref):
     many += b.process(None)
     b.close()
     assert one == many and len(one) >= 30
+
+
+def test_randomised_streams_match_reference_chain(ref):
+    """tools/stress_receive.py in small: random gaps (including none), rates, lengths, SNRs, frames cut short, scaled,
+    overlapping, loud noise bursts; the reference chain, one GPU capture and the chunked GPU chain must agree."""
+    import fun_ofdm_b200 as fo
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from stress_receive import make_stream
+    rng = np.random.default_rng(4711)
+    rx = fo.Receiver(0, 256, 4095)
+    total = 0
+    for s in range(16):
+        x, snr, nf = make_stream(ref, rng)
+        want1 = _reference_chain(ref, x, len(x))          # the whole stream in one call
+        got1, _ = rx.receive(np.concatenate([x, np.zeros(400, complex)]))
+        chunk = int(rng.choice([333, 1000, 4096, 20000]))
+        want2 = _reference_chain(ref, x, chunk)           # the reference's answer depends on the chunking (timing_sync.cpp:102)
+        ch = Chain(max_frames=256)
+        got2 = []
+        for pos in range(0, len(x), chunk):
+            got2 += ch.process(x[pos: pos + chunk])
+        for _ in range(8):
+            got2 += ch.process(np.zeros(chunk, complex))
+        ch.close()
+        assert got1 == want1, (s, len(got1), len(want1), snr)
+        assert got2 == want2, (s, chunk, len(got2), len(want2), snr)
+        total += len(want2)
+    rx.close()
+    assert total > 40
