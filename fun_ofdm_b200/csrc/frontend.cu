@@ -206,7 +206,7 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const Windo
 
 // DBG: the parity-test taps (equalised points, depunctured soft symbols) are compiled in only for calls that ask for them
 template <bool ROT, int FMT, bool DBG>
-__global__ void __launch_bounds__(FE_WARPS * 32) frontend_kernel(FrontendArgs a)
+__global__ void __launch_bounds__(FE_WARPS * 32, 5) frontend_kernel(FrontendArgs a)
 {
     __shared__ double2 s_tw[64];
     __shared__ double2 s_hinv[64];
