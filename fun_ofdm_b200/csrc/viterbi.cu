@@ -169,9 +169,9 @@ constexpr int TB_THREADS = 128;
 constexpr int TB_TILE = 96;         // decoded bits per tile (multiple of 24)
 constexpr int TB_PRE = 72;          // speculative pre-roll (multiple of 24)
 constexpr int TB_ROUNDS = (TB_TILE + TB_PRE) / 24;
-constexpr int TB_CTAS_PER_SM = 4;   // what 52 KB of shared memory per CTA allow: one full wave, no straggler CTAs
-constexpr int TB_ROW_W = 20;        // words per staged row (16 used; 80 B keeps cp.async 16-byte aligned)
-constexpr int TB_TILE_W = 4 * TB_ROW_W + 4; // words per tile slot; 84 spreads the 32 lanes of a warp over the banks
+constexpr int TB_CTAS_PER_SM = 5;   // what 44 KB of shared memory per CTA allow: one full wave, no straggler CTAs
+constexpr int TB_ROW_W = 16;        // words per staged row (64 B, all used)
+constexpr int TB_TILE_W = 4 * TB_ROW_W + 4; // words per tile slot; 68 = 4 mod 32 keeps a quarter warp's 16-byte stores on distinct banks
 constexpr int TB_MAX_BYTES = 4224;  // >= (8*(4095+6)+6+215)/8
 constexpr int TB_MAX_TILES = (TB_MAX_BYTES * 8 + TB_TILE - 1) / TB_TILE; // 352
 
