@@ -25,7 +25,9 @@ namespace b200rx {
 
 namespace {
 
-constexpr int FE_WARPS = 8;
+// Warps per frame.  Measured with six batches in flight (bench.py): 8 warps 0.936 ms per step, 4 warps 0.907 ms, 2 warps
+// 0.912 ms - small CTAs (10 per SM) interleave better with the Viterbi kernel's, and fewer warps idle while warp 0 decodes SIGNAL.
+constexpr int FE_WARPS = 4;
 constexpr int SOFT_STRIDE = 292;   // 288 soft bits + the erasure sentinel, padded to a multiple of 4
 constexpr int ERASURE_AT = 288;
 
@@ -206,7 +208,7 @@ __device__ __forceinline__ void process_symbol(const SymbolCtx &ctx, const Windo
 
 // DBG: the parity-test taps (equalised points, depunctured soft symbols) are compiled in only for calls that ask for them
 template <bool ROT, int FMT, bool DBG>
-__global__ void __launch_bounds__(FE_WARPS * 32, 5) frontend_kernel(FrontendArgs a)
+__global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(FrontendArgs a)
 {
     __shared__ double2 s_tw[64];
     __shared__ double2 s_hinv[64];
