@@ -52,13 +52,13 @@ __global__ void bm_from_symbols_kernel(const uint8_t *symbols, uint64_t symbols_
 // Per 24 steps and frame: one 96 B read of metric words (staged through shared memory, double
 // buffered, prefetched one block ahead) and three 64 B survivor stores.
 // ------------------------------------------------------------------------------------------------
-template <int LB, int RN>
-__global__ void __launch_bounds__(64) viterbi_acs2_kernel(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride,
+template <int LB, int RN, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) viterbi_acs2_kernel(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride,
                                                           uint32_t *dec, uint32_t dec_stride_words, uint32_t n_frames,
                                                           uint32_t neg1)
 {
     using A = Acs2<LB>;
-    constexpr int WARPS = 2, T = A::T, NR = A::NR, FPW = A::FPW;
+    constexpr int T = A::T, NR = A::NR, FPW = A::FPW;
     constexpr int LOADERS = 6;             // 16-byte pieces per 24 metric words
     constexpr int PER_LANE = (LOADERS + T - 1) / T; // pieces each lane of a group moves (T = 4: 2, else 1)
     __shared__ __align__(16) uint32_t s_w[WARPS][2][FPW][ACS2_BLK];
@@ -478,7 +478,13 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
     const uint32_t sched = 4u * (uint32_t)n_sm;
     int lb = (n_frames * 8u >= 32u * sched * 3u / 4u) ? 3 : 4;
     if (forced >= 2 && forced <= 4) lb = forced;
-    const uint32_t per_cta = 2u * (32u >> lb);
+    static int cta_warps = 0; // warps per CTA (B200RX_ACS_WARPS for experiments)
+    if (cta_warps == 0) {
+        const char *e = getenv("B200RX_ACS_WARPS");
+        cta_warps = e ? atoi(e) : ACS2_DEFAULT_WARPS;
+        if (cta_warps != 1 && cta_warps != 2 && cta_warps != 4) cta_warps = ACS2_DEFAULT_WARPS;
+    }
+    const uint32_t per_cta = (uint32_t)cta_warps * (32u >> lb);
     const uint32_t grid = (n_frames + per_cta - 1) / per_cta;
     static int rn = -1; // renormalisation variant (viterbi_acs2.cuh group_min), B200RX_ACS_RN for experiments
     if (rn < 0) {
@@ -486,12 +492,14 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
         rn = e ? atoi(e) : ACS2_DEFAULT_RN;
         if (rn < 0 || rn > 1) rn = ACS2_DEFAULT_RN;
     }
-#define ACS2_LAUNCH(LBV, RNV) viterbi_acs2_kernel<LBV, RNV><<<grid, 64, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu)
-#define ACS2_LAUNCH_RN(LBV) do { if (rn == 0) ACS2_LAUNCH(LBV, 0); else ACS2_LAUNCH(LBV, 1); } while (0)
+#define ACS2_LAUNCH(LBV, RNV, WV) viterbi_acs2_kernel<LBV, RNV, WV><<<grid, 32 * WV, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu)
+#define ACS2_LAUNCH_W(LBV, RNV) do { if (cta_warps == 1) ACS2_LAUNCH(LBV, RNV, 1); else if (cta_warps == 2) ACS2_LAUNCH(LBV, RNV, 2); else ACS2_LAUNCH(LBV, RNV, 4); } while (0)
+#define ACS2_LAUNCH_RN(LBV) do { if (rn == 0) ACS2_LAUNCH_W(LBV, 0); else ACS2_LAUNCH_W(LBV, 1); } while (0)
     if (lb == 2) ACS2_LAUNCH_RN(2);
     else if (lb == 3) ACS2_LAUNCH_RN(3);
     else ACS2_LAUNCH_RN(4);
 #undef ACS2_LAUNCH_RN
+#undef ACS2_LAUNCH_W
 #undef ACS2_LAUNCH
     return cudaGetLastError();
 }

@@ -37,7 +37,8 @@ namespace b200rx {
 
 constexpr int ACS2_BLK = 24;          // steps per unrolled block = lcm(6 phases, 8-step store period)
 constexpr int ACS2_WORDS_PER_8 = 16;  // survivor words per frame per 8 steps
-constexpr int ACS2_DEFAULT_RN = 1;    // renormalisation variant (Acs2::group_min)
+constexpr int ACS2_DEFAULT_RN = 1;
+constexpr int ACS2_DEFAULT_WARPS = 2; // warps per CTA of the ACS kernel    // renormalisation variant (Acs2::group_min)
 
 __host__ __device__ constexpr uint32_t acs2_rotl6(uint32_t x, int r)
 {
