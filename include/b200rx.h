@@ -119,7 +119,7 @@ B200RX_API int b200rx_synchronize(b200rx_handle *h);
 #define B200RX_FMT_SC16 2
 B200RX_API int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale);
 
-#define B200RX_MAX_PIPELINE_DEPTH 8
+#define B200RX_MAX_PIPELINE_DEPTH 12
 
 /* Pipelining of consecutive b200rx_decode_batch_dev calls.  depth = 1 (default): every call runs in order on
  * the handle's stream.  depth = 2 .. B200RX_MAX_PIPELINE_DEPTH: calls rotate over `depth` lanes, each with its own scratch set and
