@@ -4,12 +4,14 @@
  *     fft_symbols -> channel_est -> phase_tracker -> frame_decoder
  * (reference src/receiver_chain.cpp:33-36 creates them, :47-50 chains them, :106-126 drives them)
  * are replaced by one batched call that takes already-synchronised frames (the samples from each
- * frame's LTS1 tag onwards) and returns payload bytes, rate, length and a status per frame.
+ * frame's LTS1 tag onwards) and returns payload bytes, rate, length and a status per frame.  One step wider, the
+ * b200rx_receive* entry points also replace frame_detector and timing_sync (receiver_chain.cpp:31-32, 45-46), i.e. all of
+ * receiver_chain::process_samples for a contiguous capture of raw samples.
  *
  * Plain pointers and sizes only; no C++/torch types; never throws; never keeps a caller pointer
  * after the call returns.  Every entry point returns 0 on success or a negative B200RX_E_* code;
  * b200rx_last_error() gives the text.  There is NO CPU fallback: without a CUDA device of compute
- * capability 10.x b200rx_create() fails with B200RX_E_CUDA.
+ * capability 10.x b200rx_create() fails with B200RX_E_DEVICE.
  *
  * The library (fun_ofdm_b200/lib/libb200rx.so) is built by `python -c "import __graft_entry__ as g; g.build()"`
  * or `make -C fun_ofdm_b200/csrc`.
