@@ -106,15 +106,15 @@ __global__ void __launch_bounds__(32 * WARPS) viterbi_acs2_kernel(const FrameDes
                     pre[j] = __ldg(reinterpret_cast<const uint4 *>(w_in + (size_t)(b + 1) * ACS2_BLK) + piece);
             }
         }
-        uint32_t *d_blk = d_out + (size_t)b * 3 * ACS2_WORDS_PER_8 + glane * (NR / 2);
+        uint32_t *d_blk = d_out + (size_t)b * 3 * ACS2_WORDS_PER_8 + (NR >= 2 ? glane * (NR / 2) : (glane >> 1));
         const bool store = b < my_blocks;
 #pragma unroll
         for (int o = 0; o < 3; o++) {
             const uint4 wa = reinterpret_cast<const uint4 *>(sw)[2 * o];
             const uint4 wb = reinterpret_cast<const uint4 *>(sw)[2 * o + 1];
-            uint32_t acc[NR / 2];
+            uint32_t acc[A::NA];
 #pragma unroll
-            for (int j = 0; j < NR / 2; j++) acc[j] = 0;
+            for (int j = 0; j < A::NA; j++) acc[j] = 0;
             // 8 steps; phase = (8 * o + i) % 6
             if (o == 0) {
                 A::template one<0, RN>(R, acc, wa.x, L, glane, group); A::template one<1, RN>(R, acc, wa.y, L, glane, group);
@@ -132,13 +132,18 @@ __global__ void __launch_bounds__(32 * WARPS) viterbi_acs2_kernel(const FrameDes
                 A::template one<2, RN>(R, acc, wb.x, L, glane, group); A::template one<3, RN>(R, acc, wb.y, L, glane, group);
                 A::template one<4, RN>(R, acc, wb.z, L, glane, group); A::template one<5, RN>(R, acc, wb.w, L, glane, group);
             }
+#pragma unroll
+            for (int j = 0; j < A::NA; j++) acc[j] ^= L.flip[o];
+            if constexpr (NR == 1) { // lanes 2k and 2k + 1 share survivor word k: low and high 16 bits
+                const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, acc[0], 1);
+                acc[0] = (acc[0] & 0xFFFFu) | (other << 16);
+            }
             if (store) {
                 uint32_t *dst = d_blk + o * ACS2_WORDS_PER_8;
-#pragma unroll
-                for (int j = 0; j < NR / 2; j++) acc[j] ^= L.flip[o];
                 if constexpr (NR / 2 == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
                 else if constexpr (NR / 2 == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(acc[0], acc[1]);
-                else dst[0] = acc[0];
+                else if constexpr (NR == 2) dst[0] = acc[0];
+                else if ((glane & 1) == 0) dst[0] = acc[0];
             }
         }
         __syncwarp();
@@ -477,7 +482,7 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
     }
     const uint32_t sched = 4u * (uint32_t)n_sm;
     int lb = (n_frames * 8u >= 32u * sched * 3u / 4u) ? 3 : 4;
-    if (forced >= 2 && forced <= 4) lb = forced;
+    if (forced >= 2 && forced <= 5) lb = forced;
     static int cta_warps = 0; // warps per CTA (B200RX_ACS_WARPS for experiments)
     if (cta_warps == 0) {
         const char *e = getenv("B200RX_ACS_WARPS");
@@ -497,7 +502,8 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
 #define ACS2_LAUNCH_RN(LBV) do { if (rn == 0) ACS2_LAUNCH_W(LBV, 0); else ACS2_LAUNCH_W(LBV, 1); } while (0)
     if (lb == 2) ACS2_LAUNCH_RN(2);
     else if (lb == 3) ACS2_LAUNCH_RN(3);
-    else ACS2_LAUNCH_RN(4);
+    else if (lb == 4) ACS2_LAUNCH_RN(4);
+    else ACS2_LAUNCH_RN(5);
 #undef ACS2_LAUNCH_RN
 #undef ACS2_LAUNCH_W
 #undef ACS2_LAUNCH

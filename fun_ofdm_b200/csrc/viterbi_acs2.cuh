@@ -21,6 +21,10 @@
 // (acc = 2*acc + bits, one IMAD per 4 states) and stored as 64 B per frame per 8 steps; in lane phases the
 // lanes holding predecessor j+32 accumulate the complement and flip it back with one XOR before the store.
 //
+// LB = 5 (one frame per warp, two states per lane) is the low-latency end: most instructions per frame, shortest
+// dependency chain per step.  Measured on 32 .. 512 frames: 0.651 .. 0.686 ms against 0.680 .. 0.707 ms for LB = 4 - the
+// ~105 cycles a step takes are latency of the dependent DPX / shuffle / vote chain, not work, so it is only reachable
+// through B200RX_ACS_LB=5 and the launcher keeps choosing 3 or 4.
 // LB trades instructions for parallelism (ncu, 4096 frames x 12 096 steps): LB = 3 needs 11.0
 // warp-instructions per trellis step but gives 1024 warps for 592 schedulers (1 or 2 per scheduler, the
 // doubly loaded ones set the time); LB = 2 needs fewer instructions per step, has twice the independent
@@ -77,7 +81,8 @@ struct Acs2 {
     static constexpr int T = 1 << LB;       // lanes per frame
     static constexpr int NR = 32 >> LB;     // u16x2 registers per lane
     static constexpr int FPW = 32 / T;      // frames per warp
-    static_assert(LB >= 2 && LB <= 4, "2, 3 or 4 lane bits");
+    static constexpr int NA = NR >= 2 ? NR / 2 : 1; // decision accumulators per lane (NR = 1: one, 16 bits used)
+    static_assert(LB >= 2 && LB <= 5, "2 to 5 lane bits");
 
     // The class is linear in the position bits, so register i of a lane sees the lane's base class pair XOR
     // xreg(phase, i) on both halves: registers with the same xreg share one metric pair (one PRMT).
@@ -264,14 +269,18 @@ struct Acs2 {
 
     // step + decision history + renormalisation; acc[j] collects registers 2j, 2j+1
     template <int PH, int RN>
-    static __device__ __forceinline__ void one(uint32_t (&R)[NR], uint32_t (&acc)[NR / 2], uint32_t w, const Lane &L,
+    static __device__ __forceinline__ void one(uint32_t (&R)[NR], uint32_t (&acc)[NA], uint32_t w, const Lane &L,
                                                int glane, int group)
     {
         uint32_t D[NR];
         step<PH>(R, D, w, L);
         // bytes 1 and 3 of each raw decision word are 0/1: gather 4 of them, shift into the 8-step history
+        if constexpr (NR >= 2) {
 #pragma unroll
-        for (int j = 0; j < NR / 2; j++) acc[j] = acc[j] * 2u + __byte_perm(D[2 * j], D[2 * j + 1], 0x7531u);
+            for (int j = 0; j < NR / 2; j++) acc[j] = acc[j] * 2u + __byte_perm(D[2 * j], D[2 * j + 1], 0x7531u);
+        } else {
+            acc[0] = acc[0] * 2u + __byte_perm(D[0], 0u, 0x4431u); // one register: two bytes, the other two come from lane ^ 1
+        }
         renorm<RN>(R, L, group);
     }
 };
