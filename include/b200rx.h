@@ -126,7 +126,7 @@ B200RX_API int b200rx_set_sample_format(b200rx_handle *h, int format, double sc1
 /* Pipelining of consecutive b200rx_decode_batch_dev calls.  depth = 1 (default): every call runs in order on
  * the handle's stream.  depth = 2 .. B200RX_MAX_PIPELINE_DEPTH: calls rotate over `depth` lanes, each with its own scratch set and
  * stream, so that batch j+1 is already in its front end while batch j is still in its Viterbi kernel (the
- * Viterbi kernel of one 4096-frame batch cannot fill a B200: +32 % / +43 % throughput measured at depth 2 / 3).
+ * Viterbi kernel of one 4096-frame batch cannot fill a B200: +32 % / +43 % / +63 % throughput measured at depth 2 / 3 / 6).
  * A call still only reads its inputs after everything queued before it on the handle's stream, but its
  * results are ordered on that stream only after b200rx_join(); calls that may overlap (any `depth` consecutive
  * ones) must be given distinct output buffers.  b200rx_join(h, 0) makes the handle's stream wait for every
