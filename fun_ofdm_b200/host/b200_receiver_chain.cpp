@@ -14,7 +14,13 @@ namespace fun
         const uint64_t SYNC_CARRYOVER = 160; // timing_sync.h: CARRYOVER_LENGTH; tags in the last 160 samples wait (timing_sync.cpp:68)
         const uint64_t KEEP_BEFORE = 512;    // history kept in front of the first unexamined tag (detector needs 48, a tag's
                                              // LTS1 lies within [-8, +88) of it)
-        const uint64_t MAX_CAPTURE = 1u << 20; // samples per GPU pass when a caller hands over a very long vector
+        // samples per GPU pass when a caller hands over a very long vector: no more than can hold max_frames frames
+        // (the shortest frame, BPSK 1/2 with an empty payload, is 320 + 80 * 3 = 560 samples; 400 leaves a margin)
+        inline uint64_t max_capture(unsigned max_frames)
+        {
+            const uint64_t m = (uint64_t)max_frames * 400u;
+            return m < 65536u ? 65536u : (m > (1u << 22) ? (1u << 22) : m);
+        }
     }
 
     b200_receiver_chain::b200_receiver_chain(int device, unsigned max_frames, unsigned max_payload) :
@@ -77,7 +83,8 @@ namespace fun
         m_calls.push_back(m_base + m_buf_n);
         size_t fed = 0;
         do { // one GPU pass per MAX_CAPTURE new samples (normally one pass per call)
-            const size_t take = n - fed < MAX_CAPTURE ? n - fed : (size_t)MAX_CAPTURE;
+            const size_t cap = (size_t)max_capture(m_max_frames);
+            const size_t take = n - fed < cap ? n - fed : cap;
             if (!reserve(m_buf_n + take)) {
                 std::cerr << "b200_receiver_chain: out of pinned host memory" << std::endl;
                 return out;

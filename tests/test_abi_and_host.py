@@ -151,3 +151,20 @@ def test_block_adapter_compiles_against_the_reference_headers(tmp_path):
     text = open(os.path.join(ref_src, "tagged_vector.h")).read()
     for name in ("NONE", "STS_START", "STS_END", "LTS_START", "LTS1", "LTS2", "START_OF_FRAME"):
         assert name in text
+
+
+def test_host_adapters_are_inert_without_a_gpu(built):
+    """fun::b200_rx and fun::b200_receiver_chain report the missing device and produce nothing: no CPU fallback."""
+    import torch
+    _, tx = built
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = C.CDLL(tx.host_lib_path())
+    lib.b200host_chain_new.restype = C.c_void_p
+    lib.b200host_chain_new.argtypes = [C.c_int, C.c_uint, C.c_uint]
+    lib.b200host_rx_block_new.restype = C.c_void_p
+    lib.b200host_rx_block_new.argtypes = [C.c_int, C.c_uint, C.c_uint]
+    assert lib.b200host_chain_new(0, 64, 1500) is None
+    assert lib.b200host_rx_block_new(0, 64, 1500) is None
+    for name in ("b200host_chain_process", "b200host_chain_counters", "b200host_chain_delete", "b200host_rx_block_work"):
+        assert hasattr(lib, name), name
