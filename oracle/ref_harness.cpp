@@ -434,6 +434,37 @@ long ref_sync(const double *iq, long n, int chunk, double *iq_out, uint8_t *tags
     return produced;
 }
 
+/* Same, with the work() calls cut at arbitrary stream positions: call i gets samples [bounds[i], bounds[i+1]).
+ * flush_zeros > 0 appends one more call of that many zero samples, which pushes the last 160 samples out of
+ * timing_sync's carry-over.  Returns the number of output samples (n + flush_zeros). */
+long ref_sync_bounds(const double *iq, long n, const long *bounds, int n_bounds, int flush_zeros, double *iq_out,
+                     uint8_t *tags_out)
+{
+    frame_detector fd;
+    timing_sync ts;
+    long produced = 0;
+    std::vector<cd> zeros((size_t)(flush_zeros > 0 ? flush_zeros : 0));
+    for (int i = 0; i + 1 < n_bounds + (flush_zeros > 0 ? 1 : 0); i++) {
+        if (i + 1 < n_bounds) {
+            long a = std::max(0L, std::min(n, bounds[i])), e = std::max(a, std::min(n, bounds[i + 1]));
+            if (e == a) continue;
+            fd.input_buffer.assign(reinterpret_cast<const cd *>(iq) + a, reinterpret_cast<const cd *>(iq) + e);
+        } else {
+            fd.input_buffer.assign(zeros.begin(), zeros.end());
+        }
+        fd.work();
+        ts.input_buffer.swap(fd.output_buffer);
+        ts.work();
+        for (size_t k = 0; k < ts.output_buffer.size(); k++) {
+            iq_out[2 * produced] = ts.output_buffer[k].sample.real();
+            iq_out[2 * produced + 1] = ts.output_buffer[k].sample.imag();
+            tags_out[produced] = (uint8_t)ts.output_buffer[k].tag;
+            produced++;
+        }
+    }
+    return produced;
+}
+
 /* ---- tagged stream through the four hot-path blocks in chunks (streaming semantics) ---- */
 int ref_hotpath_stream(const double *iq, const uint8_t *tags, long n, int chunk,
                        uint8_t *payload_out, int payload_stride, int32_t *len_out, int max_frames)

@@ -1,0 +1,143 @@
+// TEST DOUBLE — not product code.  Implements the part of include/b200rx.h that the host adapters
+// (fun::b200_rx, fun::b200_receiver_chain) call, on the CPU, by running the UNMODIFIED reference blocks of
+// oracle/_ref/libfunref.so (dlopen).  It exists so that the adapters' bookkeeping - frame cutting, streaming state,
+// chunk boundaries, deduplication - is exercised by the CPU test stage; the GPU tests exercise the same adapters
+// against the real library.  Never linked into anything under fun_ofdm_b200/.
+#include "../../include/b200rx.h"
+
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace {
+
+struct ref_frame_info { int32_t hdr_ok, hdr_field, hdr_parity, rate_valid, rate, length, nsym, crc_ok, n_vectors, payload_from_blocks; };
+typedef int (*decode_frame_fn)(const double *, int, ref_frame_info *, double *, int, uint8_t *, uint8_t *, uint8_t *, uint8_t *,
+                               uint8_t *, uint8_t *);
+typedef long (*sync_bounds_fn)(const double *, long, const long *, int, int, double *, uint8_t *);
+
+decode_frame_fn g_decode = nullptr;
+sync_bounds_fn g_sync = nullptr;
+std::string g_err;
+
+bool load_ref()
+{
+    if (g_decode && g_sync) return true;
+    const char *path = getenv("B200RX_FAKE_REF");
+    void *so = path ? dlopen(path, RTLD_NOW | RTLD_LOCAL) : nullptr;
+    if (!so) { g_err = "fake b200rx: cannot load B200RX_FAKE_REF"; return false; }
+    g_decode = (decode_frame_fn)dlsym(so, "ref_decode_frame");
+    g_sync = (sync_bounds_fn)dlsym(so, "ref_sync_bounds");
+    if (!g_decode || !g_sync) { g_err = "fake b200rx: reference harness symbols missing"; return false; }
+    return true;
+}
+
+// one window (samples from the LTS1 tag on) through the reference's four blocks -> what the C ABI reports
+void decode_window(const double *iq, uint32_t n, uint32_t max_len, uint8_t *payload, uint16_t *len, uint8_t *rate, uint8_t *status,
+                   bool header_only)
+{
+    ref_frame_info info;
+    std::vector<uint8_t> pl(4096 + 16);
+    g_decode(iq, (int)n, &info, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, pl.data());
+    *len = 0; *rate = B200RX_RATE_INVALID;
+    if (n < 208 || info.n_vectors < 1) { *status = B200RX_ST_TRUNCATED; return; }
+    if (!info.hdr_ok) { *status = info.hdr_parity ? B200RX_ST_HDR_PARITY : B200RX_ST_HDR_RATE; return; }
+    *len = (uint16_t)info.length; *rate = (uint8_t)info.rate;
+    if ((uint32_t)info.length > max_len) { *status = B200RX_ST_TOO_LONG; return; }
+    if (header_only) { *status = B200RX_ST_OK; return; }
+    if (info.n_vectors < 1 + info.nsym) { *status = B200RX_ST_TRUNCATED; return; }
+    *status = info.crc_ok ? B200RX_ST_OK : B200RX_ST_CRC_FAIL;
+    if (info.crc_ok && payload && info.length) memcpy(payload, pl.data(), (size_t)info.length);
+}
+
+} // namespace
+
+struct b200rx_handle {
+    b200rx_limits lim;
+    std::vector<int64_t> origins;
+    std::string error;
+};
+
+extern "C" {
+
+int b200rx_create(int, const b200rx_limits *limits, b200rx_handle **out)
+{
+    if (!load_ref()) return B200RX_E_DEVICE;
+    *out = new b200rx_handle();
+    (*out)->lim = *limits;
+    return B200RX_OK;
+}
+int b200rx_destroy(b200rx_handle *h) { delete h; return B200RX_OK; }
+const char *b200rx_last_error(const b200rx_handle *h) { return h ? h->error.c_str() : g_err.c_str(); }
+const char *b200rx_version(void) { return "fake b200rx (CPU test double over oracle/_ref)"; }
+int b200rx_host_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? B200RX_OK : B200RX_E_NOMEM; }
+int b200rx_host_free(void *p) { free(p); return B200RX_OK; }
+
+int b200rx_set_receive_origins(b200rx_handle *h, const int64_t *origins, uint32_t n)
+{
+    h->origins.assign(origins, origins + n);
+    return B200RX_OK;
+}
+
+int b200rx_decode_headers(b200rx_handle *h, const void *iq, uint64_t, const uint64_t *lts1, const uint32_t *avail, uint32_t n,
+                          uint16_t *len, uint8_t *rate, uint8_t *status)
+{
+    for (uint32_t f = 0; f < n; f++)
+        decode_window((const double *)iq + 2 * lts1[f], avail[f], h->lim.max_payload_bytes, nullptr, len + f, rate + f, status + f, true);
+    return B200RX_OK;
+}
+
+int b200rx_decode_batch(b200rx_handle *h, const void *iq, uint64_t, const uint64_t *lts1, const uint32_t *avail, uint32_t n,
+                        uint8_t *payload, uint32_t stride, uint16_t *len, uint8_t *rate, uint8_t *status)
+{
+    for (uint32_t f = 0; f < n; f++)
+        decode_window((const double *)iq + 2 * lts1[f], avail[f], h->lim.max_payload_bytes, payload + (size_t)f * stride, len + f,
+                      rate + f, status + f, false);
+    return B200RX_OK;
+}
+
+// One capture through the reference's frame_detector + timing_sync (work() calls cut where the origins say the
+// reference's own calls were cut), then every LTS1-tagged window through its four hot-path blocks.
+int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n, double, uint8_t *payload, uint32_t stride, uint16_t *len,
+                   uint8_t *rate, uint8_t *status, uint64_t *lts1_out, b200rx_sync_result *res)
+{
+    memset(res, 0, sizeof(*res));
+    std::vector<long> bounds(1, 0L);
+    for (int64_t o : h->origins) {
+        const int64_t c = o + 160; // chunk start
+        if (c > bounds.back() && c < (int64_t)n) bounds.push_back((long)c);
+    }
+    bounds.push_back((long)n);
+    h->origins.clear();
+    if (n == 0) return B200RX_OK;
+    std::vector<double> out(2 * (n + 160));
+    std::vector<uint8_t> tags(n + 160);
+    const long got = g_sync((const double *)iq, (long)n, bounds.data(), (int)bounds.size(), 160, out.data(), tags.data());
+    // output index j carries stream sample j - 160; STS_END tags in the last 160 samples wait for the next capture
+    // (timing_sync.cpp:68), which here means: LTS1 tags set by events at x >= n - 160 are ignored
+    std::vector<uint64_t> starts;
+    int64_t last_event = -1;
+    for (long j = 160; j < got; j++) {
+        const uint64_t p = (uint64_t)(j - 160);
+        if (tags[j] == 2) last_event = (int64_t)p;        // STS_END
+        if (tags[j] == 4 && p < n) {                      // LTS1
+            if (last_event >= (int64_t)n - 160) continue;  // found by an event the GPU path defers
+            starts.push_back(p);
+        }
+    }
+    uint32_t nf = 0;
+    for (size_t k = 0; k < starts.size() && nf < h->lim.max_frames; k++, nf++) {
+        const uint64_t a = starts[k], e = k + 1 < starts.size() ? starts[k + 1] : n;
+        decode_window(out.data() + 2 * (a + 160), (uint32_t)(e - a), h->lim.max_payload_bytes, payload + (size_t)nf * stride,
+                      len + nf, rate + nf, status + nf, false);
+        if (lts1_out) lts1_out[nf] = a;
+    }
+    res->n_frames = nf;
+    res->overflow = (uint32_t)(starts.size() - nf);
+    return B200RX_OK;
+}
+
+} // extern "C"

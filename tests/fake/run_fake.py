@@ -1,0 +1,66 @@
+"""CPU driver of tests/test_host_logic.py (run in a subprocess: the reference chain's threads never join).
+The host adapters (fun::b200_rx, fun::b200_receiver_chain), compiled unchanged against the CPU test double of the C ABI
+(fake_b200rx.cpp -> the reference blocks of oracle/_ref), against the reference's own receiver_chain / hot-path blocks on
+the same chunked streams.  Prints one JSON object."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from oracle import bind  # noqa: E402
+
+os.environ["B200RX_FAKE_REF"] = bind.REF_SO
+FAKE_HOST = os.path.join(HERE, "_build", "libb200host_fake.so")
+
+from stress_receive import make_stream  # noqa: E402
+from test_gpu_block import Block, _stream  # noqa: E402
+from test_gpu_chain import Chain, _reference_chain  # noqa: E402
+
+
+def main():
+    ref = bind.ref()
+    out = {"chain": [], "block": []}
+    rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 11)
+    n_streams = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    for s in range(n_streams):
+        x, snr, nf = make_stream(ref, rng)
+        chunk = int(rng.choice([1000, 4096, 4096, 20000]))
+        want = _reference_chain(ref, x, chunk)
+        ch = Chain(max_frames=256, lib_path=FAKE_HOST)
+        got = []
+        for pos in range(0, len(x), chunk):
+            got += ch.process(x[pos: pos + chunk])
+        for _ in range(8):
+            got += ch.process(np.zeros(chunk, complex))
+        c = ch.counters()
+        ch.close()
+        out["chain"].append({"stream": s, "samples": len(x), "chunk": chunk, "snr": snr, "reference": [len(p) for p in want],
+                             "adapter": [len(p) for p in got], "equal": got == want, "counters": c})
+    # the block adapter on a synchronised stream (tests/test_gpu_block.py scenario)
+    for snr in (None, 25):
+        brng = np.random.default_rng(17 if snr is None else 18)
+        rates = [10, 8, 0, 5, 10, 3, 9, 6, 10, 2, 10, 10]
+        lengths = [1500, 300, 40, 700, 64, 1000, 1499, 255, 0, 120, 1500, 333]
+        x, payloads = _stream(ref, brng, rates, lengths, snr)
+        samples, tags = ref.sync(x, chunk=4096)
+        want = ref.hotpath_stream(samples, tags, chunk=4096)
+        blk = Block(lib_path=FAKE_HOST)
+        got = []
+        for s in range(0, len(tags), 4096):
+            got += blk.work(samples[s: s + 4096], tags[s: s + 4096])
+        got += blk.work(np.zeros(1, complex), np.zeros(1, np.uint8), flush=True)
+        c = blk.counters()
+        blk.close()
+        out["block"].append({"snr": snr, "reference": len(want), "adapter": len(got), "equal": got == want, "counters": c})
+    print(json.dumps(out), flush=True)
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

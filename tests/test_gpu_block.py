@@ -11,8 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class Block:
-    def __init__(self, max_frames=64, max_payload=4095):
-        self.lib = C.CDLL(os.path.join(ROOT, "fun_ofdm_b200", "lib", "libb200host.so"))
+    def __init__(self, max_frames=64, max_payload=4095, lib_path=None):
+        self.lib = C.CDLL(lib_path or os.path.join(ROOT, "fun_ofdm_b200", "lib", "libb200host.so"))
         self.lib.b200host_rx_block_new.restype = C.c_void_p
         self.lib.b200host_rx_block_new.argtypes = [C.c_int, C.c_uint, C.c_uint]
         self.lib.b200host_rx_block_work.restype = C.c_int
