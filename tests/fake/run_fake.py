@@ -58,6 +58,21 @@ def main():
         c = blk.counters()
         blk.close()
         out["block"].append({"snr": snr, "reference": len(want), "adapter": len(got), "equal": got == want, "counters": c})
+    # the block adapter on random streams tagged by the reference's own frame_detector + timing_sync
+    out["block_random"] = []
+    for s in range(n_streams):
+        x, snr, nf = make_stream(ref, rng)
+        chunk = int(rng.choice([1000, 4096, 4096, 20000]))
+        samples, tags = ref.sync(x, chunk=chunk)
+        want = ref.hotpath_stream(samples, tags, chunk=chunk)
+        blk = Block(lib_path=FAKE_HOST)
+        got = []
+        for p in range(0, len(tags), chunk):
+            got += blk.work(samples[p: p + chunk], tags[p: p + chunk])
+        got += blk.work(np.zeros(1, complex), np.zeros(1, np.uint8), flush=True)
+        blk.close()
+        out["block_random"].append({"stream": s, "chunk": chunk, "snr": snr, "reference": [len(p) for p in want],
+                                    "adapter": [len(p) for p in got], "equal": got == want})
     print(json.dumps(out), flush=True)
     os._exit(0)
 

@@ -40,6 +40,9 @@ def test_adapters_match_reference_on_chunked_streams(fake_built, seed):
     assert delivered >= 30, delivered
     for b in out["block"]:
         assert b["equal"] and b["adapter"] >= 11, b
+    assert len(out["block_random"]) == 12
+    for b in out["block_random"]:
+        assert b["equal"], b
 
 
 def test_fake_library_is_test_only():
