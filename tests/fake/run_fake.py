@@ -58,6 +58,20 @@ def main():
         c = blk.counters()
         blk.close()
         out["block"].append({"snr": snr, "reference": len(want), "adapter": len(got), "equal": got == want, "counters": c})
+    # BASELINE config 1: the test_sim loopback (examples/test_sim.cpp:43-104) through the chain adapter
+    data = b"I'm a little tea pot, short and stout.....here is my handle.....blah blah blah.....this rhyme sucks!"
+    payload = data * 15
+    frame = ref.build_frame(payload, 8)
+    x = np.concatenate([np.tile(frame, 40), np.zeros(10 * len(frame), complex)])
+    want = _reference_chain(ref, x, 4096)
+    ch = Chain(max_frames=256, lib_path=FAKE_HOST)
+    got = []
+    for pos in range(0, len(x), 4096):
+        got += ch.process(x[pos: pos + 4096])
+    got += ch.process(None)
+    ch.close()
+    out["config1"] = {"reference": len(want), "adapter": len(got), "equal": got == want,
+                      "all_equal_transmitted": all(g == payload for g in got)}
     # the block adapter on random streams tagged by the reference's own frame_detector + timing_sync
     out["block_random"] = []
     for s in range(n_streams):

@@ -40,6 +40,7 @@ def test_adapters_match_reference_on_chunked_streams(fake_built, seed):
     assert delivered >= 30, delivered
     for b in out["block"]:
         assert b["equal"] and b["adapter"] >= 11, b
+    assert out["config1"]["equal"] and out["config1"]["adapter"] == 40 and out["config1"]["all_equal_transmitted"], out["config1"]
     assert len(out["block_random"]) == 12
     for b in out["block_random"]:
         assert b["equal"], b
