@@ -168,3 +168,20 @@ def test_host_adapters_are_inert_without_a_gpu(built):
     assert lib.b200host_rx_block_new(0, 64, 1500) is None
     for name in ("b200host_chain_process", "b200host_chain_counters", "b200host_chain_delete", "b200host_rx_block_work"):
         assert hasattr(lib, name), name
+
+
+def test_device_generator_is_exported_and_fails_cleanly_without_a_gpu(built):
+    """b200tx_build_batch_dev (include/b200tx.h, B200TX_DEV_API) lives in libb200rx.so; without a device it returns -2."""
+    import torch
+    fo, tx = built
+    names = _declared("b200tx.h", "B200TX_DEV_API")
+    assert names == ["b200tx_build_batch_dev"], names
+    lib = C.CDLL(fo.lib_path())
+    fn = lib.b200tx_build_batch_dev
+    fn.restype = C.c_int
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ch = tx.Channel(25.0, 0, 0, 1, 0, 0)
+    a = (C.c_uint64 * 1)(0)
+    assert fn(0, None, None, a, a, a, 1, a, a, C.byref(ch)) == -2
+    assert fn(0, None, None, None, a, a, 1, a, a, C.byref(ch)) == -1
