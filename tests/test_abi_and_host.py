@@ -185,3 +185,16 @@ def test_device_generator_is_exported_and_fails_cleanly_without_a_gpu(built):
     a = (C.c_uint64 * 1)(0)
     assert fn(0, None, None, a, a, a, 1, a, a, C.byref(ch)) == -2
     assert fn(0, None, None, None, a, a, 1, a, a, C.byref(ch)) == -1
+
+
+@pytest.mark.parametrize("header", ["b200rx.h", "b200tx.h"])
+def test_headers_are_plain_c(header, tmp_path):
+    """The drop-in boundary is a C ABI: both headers compile as C99 with -pedantic (no C++ or CUDA types leak through)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or "/opt/gcc/bin/gcc"
+    src = tmp_path / "t.c"
+    src.write_text('#include "%s"\nint main(void) { return 0; }\n' % header)
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "t.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
