@@ -120,6 +120,8 @@ def load_library():
     L.b200rx_receive_dev.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, vp, C.POINTER(SyncResult)]
     L.b200rx_receive.restype = C.c_int
     L.b200rx_receive.argtypes = [vp, vp, u64, C.c_double, vp, u32, vp, vp, vp, vp, C.POINTER(SyncResult)]
+    L.b200rx_decode_headers.restype = C.c_int
+    L.b200rx_decode_headers.argtypes = [vp, vp, u64, vp, vp, u32, vp, vp, vp]
     L.b200rx_viterbi_batch_dev.restype = C.c_int
     L.b200rx_viterbi_batch_dev.argtypes = [vp, vp, u64, vp, u32, u32, vp, u32]
     L.b200rx_get_stats.restype = C.c_int
