@@ -8,13 +8,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
 
 using namespace b200rx;
 
-static thread_local std::string g_create_error;
+static thread_local char g_create_error[512] = {0};
 
 struct b200rx_handle {
     int device = 0;
@@ -28,11 +29,12 @@ struct b200rx_handle {
     std::vector<cudaEvent_t> ring; // 4 events per slot
     uint32_t ring_slots = 0, ring_used = 0;
 
-    // device scratch
+    // device scratch of the call being issued (one of the sets below)
     FrameDesc *desc = nullptr;
-    uint32_t *bm = nullptr;
+    uint32_t *bm = nullptr;  // front end -> ACS: metric words (4 B per step) or soft-symbol pairs (2 B per step)
     uint32_t *dec = nullptr; // survivor words: 2 per trellis step per frame
     unsigned long long *counters = nullptr; // 8 words (5 used)
+    Tuning tn;
 
     // staging of the host-buffer entry points (grow-only).  b200rx_submit_batch keeps up to B200RX_MAX_INFLIGHT calls in
     // flight, each on its own slot: staging + decode scratch + completion event.  Slot 0's scratch is lane 0's.
@@ -94,17 +96,16 @@ struct b200rx_handle {
     int sm_count = 148;
 
     uint64_t launches = 0;
-    std::string error;
+    char error_buf[512] = {0}; // what b200rx_last_error returns (no allocation on the error path)
 };
 
 namespace {
 
 int fail(b200rx_handle *h, int code, const char *what, cudaError_t ce = cudaSuccess)
 {
-    char buf[512];
-    if (ce != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s (%s)", what, cudaGetErrorString(ce), cudaGetErrorName(ce));
-    else snprintf(buf, sizeof(buf), "%s", what);
-    if (h) h->error = buf; else g_create_error = buf;
+    char *buf = h ? h->error_buf : g_create_error;
+    if (ce != cudaSuccess) snprintf(buf, 512, "%s: %s (%s)", what, cudaGetErrorString(ce), cudaGetErrorName(ce));
+    else snprintf(buf, 512, "%s", what);
     return code;
 }
 
@@ -140,7 +141,32 @@ inline int quiesce_host(b200rx_handle *h)
 }
 
 // ---- constant tables (regenerated from their defining rules; pinned by tests against the reference) ----
-bool g_tables_uploaded[64] = {false};
+std::mutex g_device_init_mutex;
+bool g_device_ready[64] = {false}; // constant tables uploaded and function attributes set, per device
+
+// one scratch set {desc, bm, dec, counters}: all four or none
+struct ScratchPtrs { FrameDesc *desc; uint32_t *bm; uint32_t *dec; unsigned long long *counters; };
+
+void free_scratch(ScratchPtrs &p)
+{
+    cudaFree(p.desc); cudaFree(p.bm); cudaFree(p.dec); cudaFree(p.counters);
+    p.desc = nullptr; p.bm = nullptr; p.dec = nullptr; p.counters = nullptr;
+}
+
+cudaError_t alloc_scratch(const b200rx_handle *h, ScratchPtrs &p)
+{
+    const size_t nf = h->limits.max_frames;
+    p.desc = nullptr; p.bm = nullptr; p.dec = nullptr; p.counters = nullptr;
+    cudaError_t e = cudaMalloc((void **)&p.desc, nf * sizeof(FrameDesc));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p.bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p.dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p.counters, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        free_scratch(p);
+        (void)cudaGetLastError();
+    }
+    return e;
+}
 
 } // namespace
 
@@ -225,7 +251,7 @@ extern "C" {
 
 const char *b200rx_version(void) { return "b200rx 0.1 (sm_100a)"; }
 
-const char *b200rx_last_error(const b200rx_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+const char *b200rx_last_error(const b200rx_handle *h) { return h ? h->error_buf : g_create_error; }
 
 int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
 {
@@ -247,15 +273,20 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
         return fail(nullptr, B200RX_E_DEVICE, buf);
     }
     CU(nullptr, cudaSetDevice(device));
-    if (!g_tables_uploaded[device & 63]) {
-        CU(nullptr, upload_tables());
-        g_tables_uploaded[device & 63] = true;
+    {
+        std::lock_guard<std::mutex> lock(g_device_init_mutex);
+        if (device >= 64 || !g_device_ready[device]) {
+            CU(nullptr, upload_tables());
+            CU(nullptr, prepare_device_functions());
+            if (device < 64) g_device_ready[device] = true;
+        }
     }
 
     b200rx_handle *h = new (std::nothrow) b200rx_handle();
     if (!h) return fail(nullptr, B200RX_E_NOMEM, "b200rx_create: out of host memory");
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    h->tn.sm_count = prop.multiProcessorCount;
     h->limits = *limits;
     h->max_steps = max_steps_for(limits->max_payload_bytes);
     const size_t nf = limits->max_frames;
@@ -268,10 +299,13 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
-    A((void **)&h->desc, nf * sizeof(FrameDesc));
-    A((void **)&h->bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
-    A((void **)&h->dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
-    A((void **)&h->counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) { // scratch set 0: lane 0 and host slot 0 share it
+        ScratchPtrs sp;
+        e = alloc_scratch(h, sp);
+        h->lanes[0].desc = sp.desc; h->lanes[0].bm = sp.bm; h->lanes[0].dec = sp.dec; h->lanes[0].counters = sp.counters;
+        h->hs[0].desc = sp.desc; h->hs[0].bm = sp.bm; h->hs[0].dec = sp.dec; h->hs[0].counters = sp.counters;
+        use_lane(h, 0);
+    }
     A((void **)&h->hs[0].d_lts1, nf * sizeof(uint64_t));
     A((void **)&h->hs[0].d_avail, nf * sizeof(uint32_t));
     A((void **)&h->hs[0].d_len, nf * sizeof(uint16_t));
@@ -280,12 +314,11 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
     if (e != cudaSuccess) {
         int code = (e == cudaErrorMemoryAllocation) ? B200RX_E_NOMEM : B200RX_E_CUDA;
         fail(nullptr, code, "b200rx_create: allocating device scratch", e);
+        (void)cudaGetLastError();
         b200rx_destroy(h);
         return code;
     }
     h->stream = h->own_stream;
-    h->lanes[0].desc = h->desc; h->lanes[0].bm = h->bm; h->lanes[0].dec = h->dec; h->lanes[0].counters = h->counters;
-    h->hs[0].desc = h->desc; h->hs[0].bm = h->bm; h->hs[0].dec = h->dec; h->hs[0].counters = h->counters;
     *out = h;
     return B200RX_OK;
 }
@@ -294,12 +327,12 @@ int b200rx_destroy(b200rx_handle *h)
 {
     if (!h) return B200RX_OK;
     cudaSetDevice(h->device);
-    if (h->stream && h->desc) cudaStreamSynchronize(h->stream);
+    if (h->stream && h->lanes[0].desc) cudaStreamSynchronize(h->stream);
     for (int i = 0; i < B200RX_MAX_PIPELINE_DEPTH; i++) {
         b200rx_handle::Lane &l = h->lanes[i];
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
         if (l.done) cudaEventDestroy(l.done);
-        if (i > 0) { cudaFree(l.desc); cudaFree(l.bm); cudaFree(l.dec); cudaFree(l.counters); }
+        cudaFree(l.desc); cudaFree(l.bm); cudaFree(l.dec); cudaFree(l.counters); // set 0 included (shared with host slot 0)
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (auto &y : h->sy) {
@@ -308,8 +341,6 @@ int b200rx_destroy(b200rx_handle *h)
     }
     for (auto p : h->d_origins) cudaFree(p);
     if (h->sy_summary_host) cudaFreeHost(h->sy_summary_host);
-    use_lane(h, 0);
-    cudaFree(h->desc); cudaFree(h->bm); cudaFree(h->dec); cudaFree(h->counters);
     for (int i = 0; i < B200RX_MAX_INFLIGHT; i++) {
         b200rx_handle::HostSlot &S = h->hs[i];
         if (S.done) { cudaEventSynchronize(S.done); cudaEventDestroy(S.done); }
@@ -326,6 +357,7 @@ int b200rx_destroy(b200rx_handle *h)
         if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    (void)cudaGetLastError();
     delete h;
     return B200RX_OK;
 }
@@ -345,6 +377,27 @@ int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale)
     if (format == B200RX_FMT_SC16 && !(sc16_scale > 0.0)) return fail(h, B200RX_E_ARG, "b200rx_set_sample_format: scale must be > 0");
     h->fmt = format;
     h->scale = format == B200RX_FMT_SC16 ? sc16_scale : 1.0;
+    return B200RX_OK;
+}
+
+int b200rx_set_tuning(b200rx_handle *h, const char *key, int64_t value)
+{
+    if (!h || !key) return B200RX_E_ARG;
+    const int v = (int)value;
+    if (!strcmp(key, "acs_gen")) { if (v != 2 && v != 3) return fail(h, B200RX_E_ARG, "b200rx_set_tuning: acs_gen is 2 or 3"); }
+    int *field = nullptr;
+    if (!strcmp(key, "acs_gen")) field = &h->tn.acs_gen;
+    else if (!strcmp(key, "acs_lb")) field = &h->tn.acs_lb;
+    else if (!strcmp(key, "acs_warps")) field = &h->tn.acs_warps;
+    else if (!strcmp(key, "acs_rn")) field = &h->tn.acs_rn;
+    else if (!strcmp(key, "h2d_chunk")) field = &h->tn.h2d_chunk;
+    else if (!strcmp(key, "h2d_chunk_min")) field = &h->tn.h2d_chunk_min;
+    else if (!strcmp(key, "pull_mode")) field = &h->tn.pull_mode;
+    else if (!strcmp(key, "fe_split")) field = &h->tn.fe_split;
+    else return fail(h, B200RX_E_ARG, "b200rx_set_tuning: unknown key");
+    int rc = b200rx_synchronize(h); // nothing in flight may see two settings
+    if (rc != B200RX_OK) return rc;
+    *field = v;
     return B200RX_OK;
 }
 
@@ -377,19 +430,17 @@ int b200rx_set_pipeline_depth(b200rx_handle *h, uint32_t depth)
     if (!h || depth < 1 || depth > B200RX_MAX_PIPELINE_DEPTH) return fail(h, B200RX_E_ARG, "b200rx_set_pipeline_depth: depth must be 1 .. B200RX_MAX_PIPELINE_DEPTH");
     int rc = b200rx_synchronize(h);
     if (rc != B200RX_OK) return rc;
-    const size_t nf = h->limits.max_frames;
     for (uint32_t i = 0; i < depth; i++) {
         b200rx_handle::Lane &l = h->lanes[i];
         if (depth > 1 && !l.stream) {
             CU(h, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
             CU(h, cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         }
-        if (i > 0 && !l.desc) {
-            cudaError_t e = cudaMalloc((void **)&l.desc, nf * sizeof(FrameDesc));
-            if (e == cudaSuccess) e = cudaMalloc((void **)&l.bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
-            if (e == cudaSuccess) e = cudaMalloc((void **)&l.dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
-            if (e == cudaSuccess) e = cudaMalloc((void **)&l.counters, 8 * sizeof(unsigned long long));
+        if (i > 0 && !l.desc) { // a lane has its whole scratch set or none of it; the depth in force stays as it was on failure
+            ScratchPtrs sp;
+            cudaError_t e = alloc_scratch(h, sp);
             if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_set_pipeline_depth: scratch for an extra lane", e);
+            l.desc = sp.desc; l.bm = sp.bm; l.dec = sp.dec; l.counters = sp.counters;
         }
     }
     if (!h->ev_in) CU(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
@@ -468,6 +519,7 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
     fa.bm_stride = h->max_steps;
     fa.max_steps = h->max_steps;
     fa.max_len = h->limits.max_payload_bytes;
+    fa.emit_pairs = h->tn.acs_gen == 3;
     fa.rot = rot_dev ? rot_dev + off : nullptr;
     fa.n_live = n_live_dev;
     if (dbg) {
@@ -479,8 +531,12 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
     if (ev) CU(h, cudaEventRecord(ev[0], s));
     CU(h, launch_frontend(fa, s));
     if (ev) CU(h, cudaEventRecord(ev[1], s));
-    CU(h, launch_viterbi_acs(h->desc + off, h->bm + (size_t)off * S, h->max_steps, h->dec + (size_t)off * 2 * S,
-                             2 * h->max_steps, n, s));
+    if (h->tn.acs_gen == 3)
+        CU(h, launch_viterbi_acs3(h->desc + off, reinterpret_cast<const uint8_t *>(h->bm + (size_t)off * S), 4 * S,
+                                  h->dec + (size_t)off * 2 * S, 2 * h->max_steps, n, false, h->tn, s));
+    else
+        CU(h, launch_viterbi_acs(h->desc + off, h->bm + (size_t)off * S, h->max_steps, h->dec + (size_t)off * 2 * S,
+                                 2 * h->max_steps, n, h->tn, s));
     if (ev) CU(h, cudaEventRecord(ev[2], s));
     TracebackArgs ta{};
     ta.desc = h->desc + off;
@@ -499,7 +555,7 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
         ta.dbg_decoded_stride = dbg->decoded_stride;
         ta.dbg_field = dbg->header_field ? dbg->header_field + off : nullptr;
     }
-    CU(h, launch_traceback(ta, s));
+    CU(h, launch_traceback(ta, h->tn, s));
     if (ev) CU(h, cudaEventRecord(ev[3], s));
     h->launches += 3;
     return B200RX_OK;
@@ -551,20 +607,27 @@ int ensure_host_slot(b200rx_handle *h, int k)
 {
     b200rx_handle::HostSlot &S = h->hs[k];
     if (!S.done) CU(h, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
-    if (S.desc) return B200RX_OK;
+    if (S.desc && S.d_status) return B200RX_OK;
     const size_t nf = h->limits.max_frames;
-    cudaError_t e = cudaSuccess;
+    // all or nothing: a slot that could not get every buffer keeps none, so a later call retries instead of launching
+    // kernels on null pointers
+    ScratchPtrs sp;
+    cudaError_t e = alloc_scratch(h, sp);
+    uint64_t *d_lts1 = nullptr; uint32_t *d_avail = nullptr; uint16_t *d_len = nullptr; uint8_t *d_rate = nullptr, *d_status = nullptr;
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    A((void **)&S.desc, nf * sizeof(FrameDesc));
-    A((void **)&S.bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
-    A((void **)&S.dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
-    A((void **)&S.counters, 8 * sizeof(unsigned long long));
-    A((void **)&S.d_lts1, nf * sizeof(uint64_t));
-    A((void **)&S.d_avail, nf * sizeof(uint32_t));
-    A((void **)&S.d_len, nf * sizeof(uint16_t));
-    A((void **)&S.d_rate, nf);
-    A((void **)&S.d_status, nf);
-    if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_submit_batch: scratch for another call in flight", e);
+    A((void **)&d_lts1, nf * sizeof(uint64_t));
+    A((void **)&d_avail, nf * sizeof(uint32_t));
+    A((void **)&d_len, nf * sizeof(uint16_t));
+    A((void **)&d_rate, nf);
+    A((void **)&d_status, nf);
+    if (e != cudaSuccess) {
+        free_scratch(sp);
+        cudaFree(d_lts1); cudaFree(d_avail); cudaFree(d_len); cudaFree(d_rate); cudaFree(d_status);
+        (void)cudaGetLastError();
+        return fail(h, B200RX_E_NOMEM, "b200rx_submit_batch: scratch for another call in flight", e);
+    }
+    S.desc = sp.desc; S.bm = sp.bm; S.dec = sp.dec; S.counters = sp.counters;
+    S.d_lts1 = d_lts1; S.d_avail = d_avail; S.d_len = d_len; S.d_rate = d_rate; S.d_status = d_status;
     return B200RX_OK;
 }
 
@@ -658,19 +721,12 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     // back.  Needs the frames in stream order (lts1_index non-decreasing); otherwise one copy, one batch.
     // The copy is the bottleneck, so what matters for one call on its own is how long the decode of the LAST chunk
     // takes after its samples have landed: chunks start at CH frames and halve towards the end (down to CH_MIN).
-    const uint32_t CH = [] { // tuning knobs for experiments
-        const char *e = getenv("B200RX_H2D_CHUNK");
-        long v = e ? atol(e) : 0;
-        return (uint32_t)(v >= 32 ? v : 1024);
-    }();
-    const uint32_t CH_MIN = [] {
-        const char *e = getenv("B200RX_H2D_CHUNK_MIN");
-        long v = e ? atol(e) : 0;
-        return (uint32_t)(v >= 16 ? v : 256);
-    }();
+    const uint32_t CH = (uint32_t)(h->tn.h2d_chunk >= 32 ? h->tn.h2d_chunk : 1024);
+    const uint32_t CH_MIN = (uint32_t)(h->tn.h2d_chunk_min >= 16 ? h->tn.h2d_chunk_min : 256);
     // Pinned caller buffer: the GPU can pull the useful samples itself (ingest.cu) instead of a DMA copy of everything.
-    const char *pull_env = getenv("B200RX_PULL"); // 0: always DMA-copy, 1: pull whenever the buffer is pinned, 2: alternate
-    const int pull_mode = pull_env ? atoi(pull_env) : (h->fmt == FMT_FC64 ? 1 : 0); // narrow formats: the DMA engine wins
+    // pull_mode 0: always DMA-copy, 1: pull whenever the buffer is pinned, 2: alternate, -1: by format (narrow formats:
+    // the DMA engine wins)
+    const int pull_mode = h->tn.pull_mode >= 0 ? h->tn.pull_mode : (h->fmt == FMT_FC64 ? 1 : 0);
     const bool pull_wanted = pull_mode != 0;
     const void *iq_mapped = nullptr;
     if (pull_wanted) {
@@ -1015,10 +1071,16 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
     cudaStream_t s = h->stream;
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     CU(h, cudaEventRecord(h->ev[0], s));
-    CU(h, launch_bm_from_symbols(symbols_dev, symbols_stride, data_bits_dev, max_data_bits, n_frames, h->desc, h->bm,
-                                 h->max_steps, h->max_steps, s));
-    CU(h, cudaEventRecord(h->ev[1], s));
-    CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, 2 * h->max_steps, n_frames, s));
+    if (h->tn.acs_gen == 3) { // the ACS kernel reads the caller's symbols in place
+        CU(h, launch_desc_from_bits(data_bits_dev, n_frames, h->desc, h->max_steps, s));
+        CU(h, cudaEventRecord(h->ev[1], s));
+        CU(h, launch_viterbi_acs3(h->desc, symbols_dev, symbols_stride, h->dec, 2 * h->max_steps, n_frames, true, h->tn, s));
+    } else {
+        CU(h, launch_bm_from_symbols(symbols_dev, symbols_stride, data_bits_dev, max_data_bits, n_frames, h->desc, h->bm,
+                                     h->max_steps, h->max_steps, s));
+        CU(h, cudaEventRecord(h->ev[1], s));
+        CU(h, launch_viterbi_acs(h->desc, h->bm, h->max_steps, h->dec, 2 * h->max_steps, n_frames, h->tn, s));
+    }
     CU(h, cudaEventRecord(h->ev[2], s));
     TracebackArgs ta{};
     ta.desc = h->desc;
@@ -1029,7 +1091,7 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
     ta.payload = out_dev;
     ta.payload_stride = out_stride;
     ta.counters = h->counters;
-    CU(h, launch_traceback(ta, s));
+    CU(h, launch_traceback(ta, h->tn, s));
     CU(h, cudaEventRecord(h->ev[3], s));
     h->ev_valid = true;
     h->launches += 3;
@@ -1039,6 +1101,7 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
 int b200rx_profile_begin(b200rx_handle *h, uint32_t slots)
 {
     if (!h) return B200RX_E_ARG;
+    if (slots > 65536) return fail(h, B200RX_E_ARG, "b200rx_profile_begin: at most 65536 slots");
     CU(h, cudaSetDevice(h->device));
     for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
     h->ring.assign(4 * (size_t)slots, nullptr);

@@ -330,11 +330,13 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(
         if constexpr (DBG) { if (a.dbg_eq && s + 1 < a.dbg_eq_vectors) dbg = a.dbg_eq + ((size_t)frame * a.dbg_eq_vectors + s + 1) * 48; }
         process_symbol<ROT, FMT, DBG>(ctx, win, 128 + 80 * (int)(s + 1) + 16, rc, (int)(s + 1), rr.bpsc, lane, dbg);
         uint32_t *sym_out = bm_out + (size_t)s * rr.dbps;
+        unsigned short *pair_out = reinterpret_cast<unsigned short *>(bm_out) + (size_t)s * rr.dbps;
         for (int t = lane; t < rr.dbps; t += 32) {
             const uint32_t pair = s_idx[t];
             const uint32_t s0 = ctx.soft[pair & 0xFFFFu], s1 = ctx.soft[pair >> 16];
             const size_t step = (size_t)s * rr.dbps + t;
-            sym_out[t] = bm_word(s0, s1);
+            if (a.emit_pairs) pair_out[t] = (unsigned short)(s0 | (s1 << 8));
+            else sym_out[t] = bm_word(s0, s1);
             if constexpr (DBG) {
                 if (a.dbg_depunct && 2 * step + 1 < a.dbg_depunct_stride) {
                     uint8_t *dp = a.dbg_depunct + (size_t)frame * a.dbg_depunct_stride + 2 * step;

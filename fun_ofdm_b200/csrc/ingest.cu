@@ -61,10 +61,7 @@ cudaError_t launch_pull(const void *src, void *dst, int fmt, uint64_t n_samples,
                         uint32_t n_frames, int sm_count, cudaStream_t s)
 {
     if (n_frames == 0) return cudaSuccess;
-    const char *e = getenv("B200RX_PULL_CTAS"); // CTAs per SM (experiments)
-    const int v = e ? atoi(e) : 0;
-    const int per_sm = v >= 1 && v <= 8 ? v : 1;
-    const uint32_t cap = (uint32_t)(sm_count * per_sm);
+    const uint32_t cap = (uint32_t)sm_count; // one CTA per SM keeps enough loads in flight to fill the PCIe link
     const unsigned grid = (unsigned)(n_frames < cap ? n_frames : cap);
     switch (fmt) {
         case FMT_FC64:

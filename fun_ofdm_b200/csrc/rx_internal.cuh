@@ -11,6 +11,7 @@ namespace b200rx {
 
 // ---- rate parameters (reference src/rates.h:52-196), indexed by fun::Rate value ----
 enum { PUNC_1_2 = 0, PUNC_2_3 = 1, PUNC_3_4 = 2 };
+enum { ACS_RN_DEFAULT = 1 };
 
 struct RateRow { uint16_t cbps, dbps; uint8_t bpsc, punc, rate_field, pad; };
 
@@ -182,6 +183,19 @@ cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s);
 uint32_t sync_cta_count(uint64_t n_samples);
 cudaError_t upload_sync_tables();
 
+// ---- per-handle tuning (b200rx_set_tuning); nothing in the launchers is process-wide ----
+struct Tuning {
+    int sm_count = 148;     // multiprocessors of the handle's device
+    int acs_gen = 3;        // ACS kernel generation: 2 = viterbi_acs2.cuh (metric words), 3 = viterbi_acs3.cuh (soft pairs)
+    int acs_lb = 0;         // lanes per frame (gen 2) / frame pair (gen 3) = 2^acs_lb; 0 = chosen from the batch size
+    int acs_warps = 0;      // warps per ACS CTA; 0 = default
+    int acs_rn = ACS_RN_DEFAULT; // gen 2: renormalisation variant
+    int h2d_chunk = 1024;   // b200rx_submit_batch: frames per pipelined chunk, and the size the last chunks shrink to
+    int h2d_chunk_min = 256;
+    int pull_mode = -1;     // host-buffer ingest: 0 DMA copy, 1 GPU pull when the buffer is pinned, 2 alternate, -1 by format
+    int fe_split = 1;       // front end: 1 = header kernel + one warp per OFDM symbol over all frames, 0 = one CTA per frame
+};
+
 // ---- launchers (each returns the cudaError_t of the launch) ----
 struct FrontendArgs {
     const void *iq;          // samples in format `fmt`
@@ -192,8 +206,9 @@ struct FrontendArgs {
     const uint32_t *avail;
     uint32_t n_frames;
     FrameDesc *desc;
-    uint32_t *bm;            // [n_frames][bm_stride] branch-metric words
+    uint32_t *bm;            // [n_frames][bm_stride] branch-metric words (ACS generation 2), or
     uint32_t bm_stride;      // words per frame (>= max_steps, multiple of 32)
+    int emit_pairs;          // 1: the same buffer receives soft-symbol pairs, 2 bytes per trellis step (ACS generation 3)
     uint32_t max_steps;
     uint32_t max_len;
     int header_only;         // 1: stop after the SIGNAL symbol (descriptor only, no branch metrics)
@@ -212,8 +227,15 @@ cudaError_t launch_bm_from_symbols(const uint8_t *symbols, uint64_t symbols_stri
                                    uint32_t max_data_bits, uint32_t n_frames, FrameDesc *desc, uint32_t *bm,
                                    uint32_t bm_stride, uint32_t max_steps, cudaStream_t s);
 
+cudaError_t launch_desc_from_bits(const uint32_t *data_bits, uint32_t n_frames, FrameDesc *desc, uint32_t max_steps, cudaStream_t s);
+
 cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride, uint32_t *dec,
-                               uint32_t dec_stride_words, uint32_t n_frames, cudaStream_t s);
+                               uint32_t dec_stride_words, uint32_t n_frames, const Tuning &tn, cudaStream_t s);
+
+// ACS generation 3: soft-symbol pairs (2 bytes per trellis step, frame f at soft + f * soft_stride bytes).  guard = the
+// buffer is the caller's: 2-byte loads and nothing is read beyond a frame's own steps.
+cudaError_t launch_viterbi_acs3(const FrameDesc *desc, const uint8_t *soft, uint64_t soft_stride, uint32_t *dec,
+                                uint32_t dec_stride_words, uint32_t n_frames, bool guard, const Tuning &tn, cudaStream_t s);
 
 struct TracebackArgs {
     FrameDesc *desc;
@@ -232,7 +254,8 @@ struct TracebackArgs {
     uint32_t *dbg_field;
 };
 
-cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s);
+cudaError_t launch_traceback(const TracebackArgs &a, const Tuning &tn, cudaStream_t s);
+cudaError_t prepare_device_functions(); // per-device function attributes; called once per device by b200rx_create
 
 cudaError_t launch_export_headers(const FrameDesc *desc, uint32_t n, uint16_t *len, uint8_t *rate, uint8_t *status,
                                   cudaStream_t s);

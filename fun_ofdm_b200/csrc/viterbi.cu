@@ -9,8 +9,7 @@
 #include "rx_internal.cuh"
 #include "viterbi_core.cuh"
 #include "viterbi_acs2.cuh"
-
-#include <stdlib.h>
+#include "viterbi_acs3.cuh"
 
 namespace b200rx {
 
@@ -151,6 +150,136 @@ __global__ void __launch_bounds__(32 * WARPS) viterbi_acs2_kernel(const FrameDes
 }
 
 // ------------------------------------------------------------------------------------------------
+// ACS, third generation (viterbi_acs3.cuh): two frames per register, 2^LB lanes per frame pair, 32 >> LB pairs per warp.
+// Input: soft-symbol pairs, 2 bytes per trellis step (frame f at soft + f * soft_stride bytes).  Per 24 steps and pair:
+// 96 B of pairs are read (prefetched one block ahead), turned into 48 metric words in shared memory (double buffered),
+// and 2 x 3 survivor rows of 64 B are stored.
+// GUARD: the buffer is the caller's (Viterbi-only entry point): 2-byte loads, nothing is read beyond a frame's n_steps.
+// ------------------------------------------------------------------------------------------------
+template <int LB, int WARPS, bool GUARD, bool LAZY>
+__global__ void __launch_bounds__(32 * WARPS) viterbi_acs3_kernel(const FrameDesc *desc, const uint8_t *soft, uint64_t soft_stride,
+                                                                  uint32_t *dec, uint32_t dec_stride_words, uint32_t n_frames,
+                                                                  uint32_t neg1)
+{
+    using A = Acs3<LB, LAZY>;
+    constexpr int T = A::T, NR = A::NR, PPW = A::PPW, NA = A::NA;
+    constexpr int SPL = 2 * ACS2_BLK / T;   // steps each lane of a pair stages per block (both frames: 48 steps)
+    static_assert(SPL % 2 == 0, "a lane stages whole 32-bit words (two steps)");
+    constexpr int WPL = SPL / 2;            // 32-bit words of pairs per lane per block
+    __shared__ __align__(16) uint32_t s_w[WARPS][2][PPW][2][ACS2_BLK];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = lane >> LB, glane = lane & (T - 1);
+    const uint32_t pair0 = (blockIdx.x * WARPS + warp) * PPW;
+    if (2u * pair0 >= n_frames) return;
+    const uint32_t fA = 2u * (pair0 + group), fB = fA + 1u;
+    const uint32_t nA = fA < n_frames ? desc[fA].n_steps : 0u;
+    const uint32_t nB = fB < n_frames ? desc[fB].n_steps : 0u;
+    const uint32_t blocksA = (nA + ACS2_BLK - 1) / ACS2_BLK, blocksB = (nB + ACS2_BLK - 1) / ACS2_BLK;
+    const uint32_t my_blocks = max(blocksA, blocksB);
+    const uint32_t n_blocks = __reduce_max_sync(0xFFFFFFFFu, my_blocks);
+    if (n_blocks == 0) return;
+
+    // staging role of this lane: the first half of the pair's lanes moves frame A, the second half frame B
+    const int st_frame = glane / (T / 2), st_part = glane % (T / 2);
+    const uint32_t st_f = st_frame ? fB : fA;
+    const uint32_t st_n = st_frame ? nB : nA;           // steps of the staged frame
+    const uint32_t st_blocks = st_frame ? blocksB : blocksA;
+    const uint8_t *st_src = soft + (size_t)min(st_f, n_frames - 1) * soft_stride + (size_t)st_part * SPL * 2;
+
+    typename A::Lane L;
+    A::lane_init(L, glane, neg1);
+    uint32_t R[NR];
+    A::init_metrics(R, glane);
+
+    uint32_t pre[WPL];
+    auto fetch = [&](uint32_t b) {
+        const uint8_t *src = st_src + (size_t)b * (ACS2_BLK * 2);
+        if constexpr (GUARD) {
+            const uint32_t s0 = b * ACS2_BLK + (uint32_t)st_part * SPL;
+#pragma unroll
+            for (int j = 0; j < WPL; j++) {
+                uint32_t lo = 0, hi = 0;
+                if (s0 + 2 * j < st_n) lo = __ldg(reinterpret_cast<const unsigned short *>(src) + 2 * j);
+                if (s0 + 2 * j + 1 < st_n) hi = __ldg(reinterpret_cast<const unsigned short *>(src) + 2 * j + 1);
+                pre[j] = lo | (hi << 16);
+            }
+        } else if constexpr (WPL % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j < WPL / 2; j++) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src) + j);
+                pre[2 * j] = v.x; pre[2 * j + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < WPL; j++) pre[j] = __ldg(reinterpret_cast<const uint32_t *>(src) + j);
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < WPL; j++) pre[j] = 0;
+    if (st_blocks > 0) fetch(0);
+
+    uint32_t *dA = dec + (size_t)min(fA, n_frames - 1) * dec_stride_words + glane * (NR / 4);
+    uint32_t *dB = dec + (size_t)min(fB, n_frames - 1) * dec_stride_words + glane * (NR / 4);
+
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        uint32_t *sw = &s_w[warp][b & 1][group][st_frame][st_part * SPL];
+#pragma unroll
+        for (int j = 0; j < WPL; j++) acs3_bm_words2(pre[j], sw[2 * j], sw[2 * j + 1]);
+        __syncwarp();
+        if (b + 1 < st_blocks) fetch(b + 1);
+        A::rebase(R, L, 20000u); // + 24 steps x 255 stays far below 0x7F2D, where the threshold constant would wrap
+        const uint32_t *swA = &s_w[warp][b & 1][group][0][0], *swB = &s_w[warp][b & 1][group][1][0];
+        const bool storeA = b < blocksA, storeB = b < blocksB;
+#pragma unroll
+        for (int o = 0; o < 3; o++) {
+            const uint4 a0 = reinterpret_cast<const uint4 *>(swA)[2 * o], a1 = reinterpret_cast<const uint4 *>(swA)[2 * o + 1];
+            const uint4 b0 = reinterpret_cast<const uint4 *>(swB)[2 * o], b1 = reinterpret_cast<const uint4 *>(swB)[2 * o + 1];
+            uint32_t acc[NA];
+#pragma unroll
+            for (int j = 0; j < NA; j++) acc[j] = 0;
+            // 8 steps; phase = (8 * o + i) % 6
+            if (o == 0) {
+                A::template one<0>(R, acc, a0.x, b0.x, L, lane); A::template one<1>(R, acc, a0.y, b0.y, L, lane);
+                A::template one<2>(R, acc, a0.z, b0.z, L, lane); A::template one<3>(R, acc, a0.w, b0.w, L, lane);
+                A::template one<4>(R, acc, a1.x, b1.x, L, lane); A::template one<5>(R, acc, a1.y, b1.y, L, lane);
+                A::template one<0>(R, acc, a1.z, b1.z, L, lane); A::template one<1>(R, acc, a1.w, b1.w, L, lane);
+            } else if (o == 1) {
+                A::template one<2>(R, acc, a0.x, b0.x, L, lane); A::template one<3>(R, acc, a0.y, b0.y, L, lane);
+                A::template one<4>(R, acc, a0.z, b0.z, L, lane); A::template one<5>(R, acc, a0.w, b0.w, L, lane);
+                A::template one<0>(R, acc, a1.x, b1.x, L, lane); A::template one<1>(R, acc, a1.y, b1.y, L, lane);
+                A::template one<2>(R, acc, a1.z, b1.z, L, lane); A::template one<3>(R, acc, a1.w, b1.w, L, lane);
+            } else {
+                A::template one<4>(R, acc, a0.x, b0.x, L, lane); A::template one<5>(R, acc, a0.y, b0.y, L, lane);
+                A::template one<0>(R, acc, a0.z, b0.z, L, lane); A::template one<1>(R, acc, a0.w, b0.w, L, lane);
+                A::template one<2>(R, acc, a1.x, b1.x, L, lane); A::template one<3>(R, acc, a1.y, b1.y, L, lane);
+                A::template one<4>(R, acc, a1.z, b1.z, L, lane); A::template one<5>(R, acc, a1.w, b1.w, L, lane);
+            }
+            // acc[j] = bytes [B of register 2j, A of 2j, B of 2j+1, A of 2j+1]; survivor word w of a frame holds
+            // positions 4w .. 4w+3 of this lane as bytes [4w+1, 4w, 4w+3, 4w+2]
+            uint32_t wa[NR / 4], wb[NR / 4];
+#pragma unroll
+            for (int w = 0; w < NR / 4; w++) {
+                wa[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x5713u) ^ L.flip[o];
+                wb[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x4602u) ^ L.flip[o];
+            }
+            uint32_t *rowA = dA + ((size_t)b * 3 + o) * ACS2_WORDS_PER_8, *rowB = dB + ((size_t)b * 3 + o) * ACS2_WORDS_PER_8;
+            if constexpr (NR / 4 == 4) {
+                if (storeA) *reinterpret_cast<uint4 *>(rowA) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                if (storeB) *reinterpret_cast<uint4 *>(rowB) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+            } else if constexpr (NR / 4 == 2) {
+                if (storeA) *reinterpret_cast<uint2 *>(rowA) = make_uint2(wa[0], wa[1]);
+                if (storeB) *reinterpret_cast<uint2 *>(rowB) = make_uint2(wb[0], wb[1]);
+            } else {
+                if (storeA) rowA[0] = wa[0];
+                if (storeB) rowB[0] = wb[0];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Traceback.  The chainback (viterbi.cpp:131-142) is a dependent chain of one step per decoded bit
 // (12 090 for a 1500-byte frame); it is cut into tiles of TB_TILE bits walked by different threads.
 // A tile starts TB_PRE steps later than it has to, from an arbitrary state (0), and relies on survivor
@@ -258,7 +387,7 @@ __device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
 
 __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TracebackArgs a)
 {
-    extern __shared__ __align__(16) uint32_t s_rows[]; // TB_THREADS * TB_TILE_W words (dynamic: > 48 KB with the rest)
+    extern __shared__ __align__(16) uint32_t s_rows[]; // TB_THREADS * TB_TILE_W words (34 KB; 44 KB with the static arrays)
     __shared__ uint8_t s_bytes[TB_MAX_BYTES];
     __shared__ uint8_t s_entry[TB_MAX_TILES + 1], s_exit[TB_MAX_TILES + 1];
     __shared__ uint32_t s_crc[4][256];
@@ -465,38 +594,41 @@ cudaError_t launch_bm_from_symbols(const uint8_t *symbols, uint64_t symbols_stri
     return cudaGetLastError();
 }
 
+// Descriptors of the Viterbi-only entry point (ACS generation 3 reads the caller's symbols in place).
+__global__ void desc_from_bits_kernel(const uint32_t *data_bits, uint32_t n_frames, FrameDesc *desc, uint32_t max_steps)
+{
+    const uint32_t frame = blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= n_frames) return;
+    const uint32_t nb = data_bits[frame];
+    const uint32_t steps = nb + 6u;
+    const bool ok = steps <= max_steps && (steps & 1u) == 0u;
+    FrameDesc d;
+    d.n_steps = ok ? steps : 0u; d.data_bits = ok ? nb : 0u; d.field = 0; d.length = 0;
+    d.rate = B200RX_RATE_INVALID; d.status = ok ? B200RX_ST_OK : B200RX_ST_TOO_LONG;
+    desc[frame] = d;
+}
+
+cudaError_t launch_desc_from_bits(const uint32_t *data_bits, uint32_t n_frames, FrameDesc *desc, uint32_t max_steps, cudaStream_t s)
+{
+    if (n_frames == 0) return cudaSuccess;
+    desc_from_bits_kernel<<<(n_frames + 127) / 128, 128, 0, s>>>(data_bits, n_frames, desc, max_steps);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32_t bm_stride, uint32_t *dec,
-                               uint32_t dec_stride_words, uint32_t n_frames, cudaStream_t s)
+                               uint32_t dec_stride_words, uint32_t n_frames, const Tuning &tn, cudaStream_t s)
 {
     if (n_frames == 0) return cudaSuccess;
     // Lanes per frame (measured on B200, 4096 frames x 12 096 steps: 4 lanes 1.19 ms, 8 lanes 0.98 ms, 16 lanes
     // 1.07 ms): 8 by default, 16 when the batch is too small to give every scheduler (4 per SM) a warp.
-    static int n_sm = 0, forced = -1;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-        const char *e = getenv("B200RX_ACS_LB");
-        forced = e ? atoi(e) : 0;
-    }
-    const uint32_t sched = 4u * (uint32_t)n_sm;
+    const uint32_t sched = 4u * (uint32_t)tn.sm_count;
     int lb = (n_frames * 8u >= 32u * sched * 3u / 4u) ? 3 : 4;
-    if (forced >= 2 && forced <= 5) lb = forced;
-    static int cta_warps = 0; // warps per CTA (B200RX_ACS_WARPS for experiments)
-    if (cta_warps == 0) {
-        const char *e = getenv("B200RX_ACS_WARPS");
-        cta_warps = e ? atoi(e) : ACS2_DEFAULT_WARPS;
-        if (cta_warps != 1 && cta_warps != 2 && cta_warps != 4) cta_warps = ACS2_DEFAULT_WARPS;
-    }
+    if (tn.acs_lb >= 2 && tn.acs_lb <= 5) lb = tn.acs_lb;
+    int cta_warps = tn.acs_warps;
+    if (cta_warps != 1 && cta_warps != 2 && cta_warps != 4) cta_warps = ACS2_DEFAULT_WARPS;
     const uint32_t per_cta = (uint32_t)cta_warps * (32u >> lb);
     const uint32_t grid = (n_frames + per_cta - 1) / per_cta;
-    static int rn = -1; // renormalisation variant (viterbi_acs2.cuh group_min), B200RX_ACS_RN for experiments
-    if (rn < 0) {
-        const char *e = getenv("B200RX_ACS_RN");
-        rn = e ? atoi(e) : ACS2_DEFAULT_RN;
-        if (rn < 0 || rn > 1) rn = ACS2_DEFAULT_RN;
-    }
+    const int rn = (tn.acs_rn == 0) ? 0 : 1;
 #define ACS2_LAUNCH(LBV, RNV, WV) viterbi_acs2_kernel<LBV, RNV, WV><<<grid, 32 * WV, 0, s>>>(desc, bm, bm_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu)
 #define ACS2_LAUNCH_W(LBV, RNV) do { if (cta_warps == 1) ACS2_LAUNCH(LBV, RNV, 1); else if (cta_warps == 2) ACS2_LAUNCH(LBV, RNV, 2); else ACS2_LAUNCH(LBV, RNV, 4); } while (0)
 #define ACS2_LAUNCH_RN(LBV) do { if (rn == 0) ACS2_LAUNCH_W(LBV, 0); else ACS2_LAUNCH_W(LBV, 1); } while (0)
@@ -507,6 +639,32 @@ cudaError_t launch_viterbi_acs(const FrameDesc *desc, const uint32_t *bm, uint32
 #undef ACS2_LAUNCH_RN
 #undef ACS2_LAUNCH_W
 #undef ACS2_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_viterbi_acs3(const FrameDesc *desc, const uint8_t *soft, uint64_t soft_stride, uint32_t *dec,
+                                uint32_t dec_stride_words, uint32_t n_frames, bool guard, const Tuning &tn, cudaStream_t s)
+{
+    if (n_frames == 0) return cudaSuccess;
+    // Lanes per frame pair: 4 (16 frames per warp) once the batch gives every scheduler a warp that way, else 8.
+    const uint32_t sched = 4u * (uint32_t)tn.sm_count;
+    int lb = (n_frames >= 16u * sched * 3u / 4u) ? 2 : 3;
+    if (tn.acs_lb >= 1 && tn.acs_lb <= 3) lb = tn.acs_lb;
+    int cta_warps = tn.acs_warps;
+    if (cta_warps != 1 && cta_warps != 2 && cta_warps != 4) cta_warps = 1;
+    const uint32_t per_cta = (uint32_t)cta_warps * (64u >> lb); // frames per CTA
+    const uint32_t grid = (n_frames + per_cta - 1) / per_cta;
+#define ACS3_LAUNCH(LBV, WV, GV, ZV) viterbi_acs3_kernel<LBV, WV, GV, ZV><<<grid, 32 * WV, 0, s>>>(desc, soft, soft_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu)
+#define ACS3_LAUNCH_Z(LBV, WV, GV) do { if (tn.acs_rn == 0) ACS3_LAUNCH(LBV, WV, GV, false); else ACS3_LAUNCH(LBV, WV, GV, true); } while (0)
+#define ACS3_LAUNCH_G(LBV, WV) do { if (guard) ACS3_LAUNCH_Z(LBV, WV, true); else ACS3_LAUNCH_Z(LBV, WV, false); } while (0)
+#define ACS3_LAUNCH_W(LBV) do { if (cta_warps == 1) ACS3_LAUNCH_G(LBV, 1); else if (cta_warps == 2) ACS3_LAUNCH_G(LBV, 2); else ACS3_LAUNCH_G(LBV, 4); } while (0)
+    if (lb == 1) ACS3_LAUNCH_W(1);
+    else if (lb == 2) ACS3_LAUNCH_W(2);
+    else ACS3_LAUNCH_W(3);
+#undef ACS3_LAUNCH_W
+#undef ACS3_LAUNCH_G
+#undef ACS3_LAUNCH_Z
+#undef ACS3_LAUNCH
     return cudaGetLastError();
 }
 
@@ -529,24 +687,17 @@ cudaError_t launch_export_headers(const FrameDesc *desc, uint32_t n, uint16_t *l
     return cudaGetLastError();
 }
 
-cudaError_t launch_traceback(const TracebackArgs &a, cudaStream_t s)
+cudaError_t prepare_device_functions()
+{
+    constexpr size_t dyn = sizeof(uint32_t) * TB_THREADS * TB_TILE_W;
+    return cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+}
+
+cudaError_t launch_traceback(const TracebackArgs &a, const Tuning &tn, cudaStream_t s)
 {
     if (a.n_frames == 0) return cudaSuccess;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
     constexpr size_t dyn = sizeof(uint32_t) * TB_THREADS * TB_TILE_W;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    const uint32_t grid = min((uint32_t)(n_sm * TB_CTAS_PER_SM), a.n_frames);
+    const uint32_t grid = min((uint32_t)(tn.sm_count * TB_CTAS_PER_SM), a.n_frames);
     traceback_kernel<<<grid, TB_THREADS, dyn, s>>>(a);
     return cudaGetLastError();
 }

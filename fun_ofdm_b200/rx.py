@@ -94,6 +94,8 @@ def load_library():
     L.b200rx_synchronize.argtypes = [vp]
     L.b200rx_set_sample_format.restype = C.c_int
     L.b200rx_set_sample_format.argtypes = [vp, C.c_int, C.c_double]
+    L.b200rx_set_tuning.restype = C.c_int
+    L.b200rx_set_tuning.argtypes = [vp, C.c_char_p, C.c_int64]
     L.b200rx_set_pipeline_depth.restype = C.c_int
     L.b200rx_set_pipeline_depth.argtypes = [vp, u32]
     L.b200rx_join.restype = C.c_int
@@ -202,6 +204,10 @@ class Receiver:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.b200rx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or None)), "b200rx_set_stream")
+
+    def set_tuning(self, key, value):
+        """Implementation knob of the handle (include/b200rx.h, b200rx_set_tuning); never changes results."""
+        self._check(self.lib.b200rx_set_tuning(self.h, key.encode(), int(value)), "b200rx_set_tuning")
 
     def set_pipeline_depth(self, depth):
         self._check(self.lib.b200rx_set_pipeline_depth(self.h, int(depth)), "b200rx_set_pipeline_depth")

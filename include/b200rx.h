@@ -121,6 +121,19 @@ B200RX_API int b200rx_synchronize(b200rx_handle *h);
 #define B200RX_FMT_SC16 2
 B200RX_API int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale);
 
+/* Implementation knobs, per handle (nothing is read from the environment).  Results never depend on them; they select
+ * between kernel variants and pipeline geometries that are bit-identical by construction and by test.  Keys:
+ *   "acs_gen"       3 (default): add-compare-select on soft-symbol pairs, two frames per register; 2: round-1 kernel
+ *   "acs_lb"        log2 of the lanes per frame (gen 2: 2..5) / per frame pair (gen 3: 1..3); 0 = from the batch size
+ *   "acs_warps"     warps per ACS CTA (1, 2, 4); 0 = default
+ *   "acs_rn"        renormalisation variant: gen 2 cross-lane minimum in 1 (0) or 2 (1) lane bits per round; gen 3
+ *                   subtract the minimum (0) or keep a per-frame offset (1, default)
+ *   "h2d_chunk", "h2d_chunk_min"   frames per pipelined chunk of b200rx_submit_batch
+ *   "pull_mode"     host-buffer ingest: 0 DMA copy, 1 GPU pull from pinned memory, 2 alternate, -1 by sample format
+ *   "fe_split"      front end: 1 header kernel + one warp per OFDM symbol (default), 0 one CTA per frame
+ * The call drains the handle first. */
+B200RX_API int b200rx_set_tuning(b200rx_handle *h, const char *key, int64_t value);
+
 #define B200RX_MAX_PIPELINE_DEPTH 12
 
 /* Pipelining of consecutive b200rx_decode_batch_dev calls.  depth = 1 (default): every call runs in order on

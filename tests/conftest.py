@@ -12,12 +12,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def _gpu_run(config):
+    """True when the GPU tests are selected (`-m gpu`): there a missing checker is a failure, never a skip."""
+    expr = config.getoption("-m") or ""
+    return "gpu" in expr and "not gpu" not in expr
+
+
 @pytest.fixture(scope="session")
-def ref():
-    """The unmodified reference compiled under oracle/_ref (checker)."""
+def ref(request):
+    """The unmodified reference compiled under oracle/_ref (checker).  The library is built here (where /root/reference
+    exists) and travels to the GPU box with the repository snapshot; a GPU run without it cannot prove parity, so it
+    fails instead of quietly dropping to the committed fixtures."""
     from oracle import bind
     if not bind.have_ref():
-        pytest.skip("oracle/_ref/libfunref.so not built (needs /root/reference; run `make -C oracle ref`)")
+        msg = "oracle/_ref/libfunref.so not built (needs /root/reference; run `make -C oracle ref`)"
+        if _gpu_run(request.config):
+            pytest.fail("parity checker missing under -m gpu: " + msg, pytrace=False)
+        pytest.skip(msg)
     return bind.ref()
 
 

@@ -51,6 +51,19 @@ __global__ void bench(uint32_t *out, long long *cyc, uint32_t seed, uint32_t neg
             if (MODE == 9) { r[i] = __viaddmin_u16x2(r[i], q[i], 0x00FF00FFu); q[i] = imad(q[i], neg1, r[i]); r[i] ^= hset_eq(q[i], r[i]) & 1; } // DPX+IMAD+HSET2+LOP
             if (MODE == 10) r[i] = __vminu2(r[i], q[i]);                                        // VIMNMX
             if (MODE == 11) r[i] = __vimin3_u16x2(r[i], q[i], r[(i + 1) % CH]);                 // VIMNMX3
+            if (MODE == 12) { r[i] = __viaddmin_u16x2(r[i], q[i], 0x00FF00FFu); q[i] = __vminu2(q[i], r[i]); }                         // DPX + VIMNMX
+            if (MODE == 13) { r[i] = imad(r[i], neg1, q[i]); q[i] = __vminu2(q[i], r[i]); }                                            // IMAD + VIMNMX
+            if (MODE == 14) { r[i] = __viaddmin_u16x2(r[i], q[i], 0x00FF00FFu); q[i] = imad(q[i], neg1, r[i]); r[i] = __vminu2(q[i], r[i]); } // DPX + IMAD + VIMNMX
+            if (MODE == 15) r[i] = r[i] + q[i] + seed;                                           // IADD3
+            if (MODE == 16) r[i] = (r[i] & q[i]) ^ seed;                                          // LOP3
+            if (MODE == 17) { r[i] = __viaddmin_u16x2(r[i], q[i], 0x00FF00FFu); q[i] = (q[i] & r[i]) ^ seed; }                         // DPX + LOP3
+            if (MODE == 18) { r[i] = imad(r[i], neg1, q[i]); q[i] = (q[i] & r[i]) ^ seed; }                                            // IMAD + LOP3
+            if (MODE == 19) { r[i] = __viaddmin_u16x2(r[i], q[i], 0x00FF00FFu); q[i] = imad(q[i], neg1, r[i]); q[i] = imad(q[i], neg1, r[i]); } // DPX + 2 IMAD
+            if (MODE == 20) { uint32_t t = __viaddmin_u16x2(q[i], r[i], 0x00FF00FFu); r[i] = __viaddmin_u16x2(r[i], q[i], t); q[i] = imad(r[i], seed, imad(t, neg1, 0x01000100u)); } // acs2 register phase
+            if (MODE == 21) { uint32_t t = __viaddmin_u16x2(q[i], r[i], 0x00FF00FFu); r[i] = __viaddmin_u16x2(r[i], q[i], t); q[i] = imad(q[i], 2u, hset_eq(r[i], t)); } // acs3 register phase
+            if (MODE == 22) { uint32_t t = __viaddmin_u16x2(q[i], r[i], 0x00FF00FFu); r[i] = __viaddmin_u16x2(r[i], q[i], t); q[i] = imad(q[i], 2u, r[i] + 0x01000100u - t); } // IADD3 decisions
+            if (MODE == 23) r[i] = __vmaxu2(r[i], q[i]) + (r[i] > q[i] ? 1 : 0);                   // VIMNMX + ISETP/SEL
+            if (MODE == 24) r[i] = __hmin2(*(__half2*)&r[i], *(__half2*)&q[i]).x > (__half)0 ? r[i] : q[i]; // filler
         }
     }
     long long t1 = clock64();
@@ -115,6 +128,17 @@ int main()
     run<7>("IMAD + HSET2", 2);
     run<8>("VIADDMNMX + SHFL", 2);
     run<9>("VIADDMNMX+IMAD+HSET2+LOP3", 4);
+    run<12>("VIADDMNMX + VIMNMX", 2);
+    run<13>("IMAD + VIMNMX", 2);
+    run<14>("VIADDMNMX + IMAD + VIMNMX", 3);
+    run<15>("IADD3", 1);
+    run<16>("LOP3", 1);
+    run<17>("VIADDMNMX + LOP3", 2);
+    run<18>("IMAD + LOP3", 2);
+    run<19>("VIADDMNMX + 2 IMAD", 3);
+    run<20>("reg phase: 2 DPX + 2 IMAD", 4);
+    run<21>("reg phase: 2 DPX + HSET2 + IMAD", 4);
+    run<22>("reg phase: 2 DPX + IADD3 + IMAD", 4);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
