@@ -156,8 +156,11 @@ __global__ void __launch_bounds__(32 * WARPS) viterbi_acs2_kernel(const FrameDes
 // and 2 x 3 survivor rows of 64 B are stored.
 // GUARD: the buffer is the caller's (Viterbi-only entry point): 2-byte loads, nothing is read beyond a frame's n_steps.
 // ------------------------------------------------------------------------------------------------
+// Registers: 128 per thread at LB = 2 (16 warps per SM), 96 at LB = 3.  Capping LB = 2 at 96 as well compiles without spills
+// but schedules worse: 0.892 instead of 0.823 ms per pipelined step (bench.py, 12 batches in flight).
+constexpr int acs3_min_warps_per_sm(int lb) { return lb <= 2 ? 16 : 20; }
 template <int LB, int WARPS, bool GUARD, bool LAZY>
-__global__ void __launch_bounds__(32 * WARPS) viterbi_acs3_kernel(const FrameDesc *desc, const uint8_t *soft, uint64_t soft_stride,
+__global__ void __launch_bounds__(32 * WARPS, acs3_min_warps_per_sm(LB) / WARPS) viterbi_acs3_kernel(const FrameDesc *desc, const uint8_t *soft, uint64_t soft_stride,
                                                                   uint32_t *dec, uint32_t dec_stride_words, uint32_t n_frames,
                                                                   uint32_t neg1)
 {
@@ -166,7 +169,10 @@ __global__ void __launch_bounds__(32 * WARPS) viterbi_acs3_kernel(const FrameDes
     constexpr int SPL = 2 * ACS2_BLK / T;   // steps each lane of a pair stages per block (both frames: 48 steps)
     static_assert(SPL % 2 == 0, "a lane stages whole 32-bit words (two steps)");
     constexpr int WPL = SPL / 2;            // 32-bit words of pairs per lane per block
-    __shared__ __align__(16) uint32_t s_w[WARPS][2][PPW][2][ACS2_BLK];
+    // 2 x 24 words per pair + 4 words of padding: the pairs of a warp read the same word index at the same time, and a
+    // stride of 48 words puts every other pair on the same banks (ncu: 4-way conflicts on the metric loads)
+    constexpr int PAIR_W = 2 * ACS2_BLK + 4;
+    __shared__ __align__(16) uint32_t s_w[WARPS][2][PPW][PAIR_W];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = lane >> LB, glane = lane & (T - 1);
@@ -219,61 +225,63 @@ __global__ void __launch_bounds__(32 * WARPS) viterbi_acs3_kernel(const FrameDes
     for (int j = 0; j < WPL; j++) pre[j] = 0;
     if (st_blocks > 0) fetch(0);
 
+    uint32_t acc[NA];
+#pragma unroll
+    for (int j = 0; j < NA; j++) acc[j] = 0;
     uint32_t *dA = dec + (size_t)min(fA, n_frames - 1) * dec_stride_words + glane * (NR / 4);
     uint32_t *dB = dec + (size_t)min(fB, n_frames - 1) * dec_stride_words + glane * (NR / 4);
 
     for (uint32_t b = 0; b < n_blocks; b++) {
-        uint32_t *sw = &s_w[warp][b & 1][group][st_frame][st_part * SPL];
+        uint32_t *sw = &s_w[warp][b & 1][group][st_frame * ACS2_BLK + st_part * SPL];
 #pragma unroll
         for (int j = 0; j < WPL; j++) acs3_bm_words2(pre[j], sw[2 * j], sw[2 * j + 1]);
         __syncwarp();
         if (b + 1 < st_blocks) fetch(b + 1);
         A::rebase(R, L, 20000u); // + 24 steps x 255 stays far below 0x7F2D, where the threshold constant would wrap
-        const uint32_t *swA = &s_w[warp][b & 1][group][0][0], *swB = &s_w[warp][b & 1][group][1][0];
+        const uint32_t *swA = &s_w[warp][b & 1][group][0], *swB = &s_w[warp][b & 1][group][ACS2_BLK];
         const bool storeA = b < blocksA, storeB = b < blocksB;
-#pragma unroll
-        for (int o = 0; o < 3; o++) {
-            const uint4 a0 = reinterpret_cast<const uint4 *>(swA)[2 * o], a1 = reinterpret_cast<const uint4 *>(swA)[2 * o + 1];
-            const uint4 b0 = reinterpret_cast<const uint4 *>(swB)[2 * o], b1 = reinterpret_cast<const uint4 *>(swB)[2 * o + 1];
-            uint32_t acc[NA];
-#pragma unroll
-            for (int j = 0; j < NA; j++) acc[j] = 0;
-            // 8 steps; phase = (8 * o + i) % 6
-            if (o == 0) {
-                A::template one<0>(R, acc, a0.x, b0.x, L, lane); A::template one<1>(R, acc, a0.y, b0.y, L, lane);
-                A::template one<2>(R, acc, a0.z, b0.z, L, lane); A::template one<3>(R, acc, a0.w, b0.w, L, lane);
-                A::template one<4>(R, acc, a1.x, b1.x, L, lane); A::template one<5>(R, acc, a1.y, b1.y, L, lane);
-                A::template one<0>(R, acc, a1.z, b1.z, L, lane); A::template one<1>(R, acc, a1.w, b1.w, L, lane);
-            } else if (o == 1) {
-                A::template one<2>(R, acc, a0.x, b0.x, L, lane); A::template one<3>(R, acc, a0.y, b0.y, L, lane);
-                A::template one<4>(R, acc, a0.z, b0.z, L, lane); A::template one<5>(R, acc, a0.w, b0.w, L, lane);
-                A::template one<0>(R, acc, a1.x, b1.x, L, lane); A::template one<1>(R, acc, a1.y, b1.y, L, lane);
-                A::template one<2>(R, acc, a1.z, b1.z, L, lane); A::template one<3>(R, acc, a1.w, b1.w, L, lane);
-            } else {
-                A::template one<4>(R, acc, a0.x, b0.x, L, lane); A::template one<5>(R, acc, a0.y, b0.y, L, lane);
-                A::template one<0>(R, acc, a0.z, b0.z, L, lane); A::template one<1>(R, acc, a0.w, b0.w, L, lane);
-                A::template one<2>(R, acc, a1.x, b1.x, L, lane); A::template one<3>(R, acc, a1.y, b1.y, L, lane);
-                A::template one<4>(R, acc, a1.z, b1.z, L, lane); A::template one<5>(R, acc, a1.w, b1.w, L, lane);
-            }
-            // acc[j] = bytes [B of register 2j, A of 2j, B of 2j+1, A of 2j+1]; survivor word w of a frame holds
-            // positions 4w .. 4w+3 of this lane as bytes [4w+1, 4w, 4w+3, 4w+2]
+        uint32_t *rowA = dA + (size_t)b * 3 * ACS2_WORDS_PER_8, *rowB = dB + (size_t)b * 3 * ACS2_WORDS_PER_8;
+        // acc[j] = bytes [B of register 2j, A of 2j, B of 2j+1, A of 2j+1]; survivor word w of a frame holds positions
+        // 4w .. 4w+3 of this lane as bytes [4w+1, 4w, 4w+3, 4w+2]
+        auto store = [&](int o) {
             uint32_t wa[NR / 4], wb[NR / 4];
 #pragma unroll
             for (int w = 0; w < NR / 4; w++) {
                 wa[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x5713u) ^ L.flip[o];
                 wb[w] = __byte_perm(acc[2 * w], acc[2 * w + 1], 0x4602u) ^ L.flip[o];
             }
-            uint32_t *rowA = dA + ((size_t)b * 3 + o) * ACS2_WORDS_PER_8, *rowB = dB + ((size_t)b * 3 + o) * ACS2_WORDS_PER_8;
-            if constexpr (NR / 4 == 4) {
-                if (storeA) *reinterpret_cast<uint4 *>(rowA) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
-                if (storeB) *reinterpret_cast<uint4 *>(rowB) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
-            } else if constexpr (NR / 4 == 2) {
-                if (storeA) *reinterpret_cast<uint2 *>(rowA) = make_uint2(wa[0], wa[1]);
-                if (storeB) *reinterpret_cast<uint2 *>(rowB) = make_uint2(wb[0], wb[1]);
+            uint32_t *ra = rowA + o * ACS2_WORDS_PER_8, *rb = rowB + o * ACS2_WORDS_PER_8;
+            if constexpr (NR / 4 == 8) {
+                if (storeA) { reinterpret_cast<uint4 *>(ra)[0] = make_uint4(wa[0], wa[1], wa[2], wa[3]); reinterpret_cast<uint4 *>(ra)[1] = make_uint4(wa[4], wa[5], wa[6], wa[7]); }
+                if (storeB) { reinterpret_cast<uint4 *>(rb)[0] = make_uint4(wb[0], wb[1], wb[2], wb[3]); reinterpret_cast<uint4 *>(rb)[1] = make_uint4(wb[4], wb[5], wb[6], wb[7]); }
+            } else if constexpr (NR / 4 == 4) {
+                if (storeA) *reinterpret_cast<uint4 *>(ra) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                if (storeB) *reinterpret_cast<uint4 *>(rb) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
             } else {
-                if (storeA) rowA[0] = wa[0];
-                if (storeB) rowB[0] = wb[0];
+                if (storeA) *reinterpret_cast<uint2 *>(ra) = make_uint2(wa[0], wa[1]);
+                if (storeB) *reinterpret_cast<uint2 *>(rb) = make_uint2(wb[0], wb[1]);
             }
+#pragma unroll
+            for (int j = 0; j < NA; j++) acc[j] = 0;
+        };
+        // The unrolled body is one phase cycle (6 steps), not the 24-step block: with 64 >> LB state registers per lane a
+        // 24-step body is 30-50 KB of code and ncu showed the warps waiting for instruction fetches (stall_no_instruction
+        // 0.87 per issue at LB = 2).  Survivor rows are 8 steps, so a row ends inside cycles 1, 2 and at the end of cycle 3.
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            const uint2 a01 = reinterpret_cast<const uint2 *>(swA)[3 * c], a23 = reinterpret_cast<const uint2 *>(swA)[3 * c + 1],
+                        a45 = reinterpret_cast<const uint2 *>(swA)[3 * c + 2];
+            const uint2 b01 = reinterpret_cast<const uint2 *>(swB)[3 * c], b23 = reinterpret_cast<const uint2 *>(swB)[3 * c + 1],
+                        b45 = reinterpret_cast<const uint2 *>(swB)[3 * c + 2];
+            A::template one<0>(R, acc, a01.x, b01.x, L, lane);
+            A::template one<1>(R, acc, a01.y, b01.y, L, lane);
+            if (c == 1) store(0);
+            A::template one<2>(R, acc, a23.x, b23.x, L, lane);
+            A::template one<3>(R, acc, a23.y, b23.y, L, lane);
+            if (c == 2) store(1);
+            A::template one<4>(R, acc, a45.x, b45.x, L, lane);
+            A::template one<5>(R, acc, a45.y, b45.y, L, lane);
+            if (c == 3) store(2);
         }
         __syncwarp();
     }
@@ -648,18 +656,18 @@ cudaError_t launch_viterbi_acs3(const FrameDesc *desc, const uint8_t *soft, uint
     if (n_frames == 0) return cudaSuccess;
     // Lanes per frame pair: 4 (16 frames per warp) once the batch gives every scheduler a warp that way, else 8.
     const uint32_t sched = 4u * (uint32_t)tn.sm_count;
+    // (bench.py, config 2, 12 batches in flight: LB = 2 with 4-warp CTAs 0.797 ms per step, 2-warp CTAs 0.82-0.84, LB = 3 0.844)
     int lb = (n_frames >= 16u * sched * 3u / 4u) ? 2 : 3;
-    if (tn.acs_lb >= 1 && tn.acs_lb <= 3) lb = tn.acs_lb;
+    if (tn.acs_lb >= 2 && tn.acs_lb <= 3) lb = tn.acs_lb;
     int cta_warps = tn.acs_warps;
-    if (cta_warps != 1 && cta_warps != 2 && cta_warps != 4) cta_warps = 1;
+    if (cta_warps != 1 && cta_warps != 2 && cta_warps != 4) cta_warps = 4;
     const uint32_t per_cta = (uint32_t)cta_warps * (64u >> lb); // frames per CTA
     const uint32_t grid = (n_frames + per_cta - 1) / per_cta;
 #define ACS3_LAUNCH(LBV, WV, GV, ZV) viterbi_acs3_kernel<LBV, WV, GV, ZV><<<grid, 32 * WV, 0, s>>>(desc, soft, soft_stride, dec, dec_stride_words, n_frames, 0xFFFFFFFFu)
 #define ACS3_LAUNCH_Z(LBV, WV, GV) do { if (tn.acs_rn == 0) ACS3_LAUNCH(LBV, WV, GV, false); else ACS3_LAUNCH(LBV, WV, GV, true); } while (0)
 #define ACS3_LAUNCH_G(LBV, WV) do { if (guard) ACS3_LAUNCH_Z(LBV, WV, true); else ACS3_LAUNCH_Z(LBV, WV, false); } while (0)
 #define ACS3_LAUNCH_W(LBV) do { if (cta_warps == 1) ACS3_LAUNCH_G(LBV, 1); else if (cta_warps == 2) ACS3_LAUNCH_G(LBV, 2); else ACS3_LAUNCH_G(LBV, 4); } while (0)
-    if (lb == 1) ACS3_LAUNCH_W(1);
-    else if (lb == 2) ACS3_LAUNCH_W(2);
+    if (lb == 2) ACS3_LAUNCH_W(2);
     else ACS3_LAUNCH_W(3);
 #undef ACS3_LAUNCH_W
 #undef ACS3_LAUNCH_G

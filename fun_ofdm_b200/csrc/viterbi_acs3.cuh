@@ -246,10 +246,12 @@ __device__ __forceinline__ void acs3_bm_words2(uint32_t x, uint32_t &w0, uint32_
     const uint32_t X1 = __byte_perm(x, 0u, 0x4341u);          // s1 | s1' << 16
     const uint32_t a = X0 + X1 + 0x00010001u;                 // s0 + s1 + 1            (1 .. 511 per half)
     const uint32_t d = X0 - X1 + 0x01000100u;                 // s0 - s1 + 256          (1 .. 511 per half)
-    const uint32_t m00 = (a >> 3) & 0x003F003Fu;
-    const uint32_t m11 = ((0x02000200u - a) >> 3) & 0x003F003Fu;
-    const uint32_t m01 = (d >> 3) & 0x003F003Fu;
-    const uint32_t m10 = ((0x02000200u - d) >> 3) & 0x003F003Fu;
+    // (x >> 3) per half: the 6-bit result sits in the low byte of the half; what the shift drags into the byte above it is
+    // never selected below
+    const uint32_t m00 = a >> 3;
+    const uint32_t m11 = (0x02000200u - a) >> 3;
+    const uint32_t m01 = d >> 3;
+    const uint32_t m10 = (0x02000200u - d) >> 3;
     const uint32_t U = __byte_perm(m00, m01, 0x6240u);        // m00, m01, m00', m01'
     const uint32_t V = __byte_perm(m10, m11, 0x6240u);        // m10, m11, m10', m11'
     w0 = __byte_perm(U, V, 0x5410u);

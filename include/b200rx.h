@@ -124,7 +124,7 @@ B200RX_API int b200rx_set_sample_format(b200rx_handle *h, int format, double sc1
 /* Implementation knobs, per handle (nothing is read from the environment).  Results never depend on them; they select
  * between kernel variants and pipeline geometries that are bit-identical by construction and by test.  Keys:
  *   "acs_gen"       3 (default): add-compare-select on soft-symbol pairs, two frames per register; 2: round-1 kernel
- *   "acs_lb"        log2 of the lanes per frame (gen 2: 2..5) / per frame pair (gen 3: 1..3); 0 = from the batch size
+ *   "acs_lb"        log2 of the lanes per frame (gen 2: 2..5) / per frame pair (gen 3: 2..3); 0 = from the batch size
  *   "acs_warps"     warps per ACS CTA (1, 2, 4); 0 = default
  *   "acs_rn"        renormalisation variant: gen 2 cross-lane minimum in 1 (0) or 2 (1) lane bits per round; gen 3
  *                   subtract the minimum (0) or keep a per-frame offset (1, default)

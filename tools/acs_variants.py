@@ -39,7 +39,9 @@ def main():
     variants = [dict(acs_gen=2, acs_lb=3, acs_warps=2, acs_rn=1)]
     for lb in (2, 3, 1):
         for rn in (1, 0):
-            for w in (1, 2, 4):
+            for w in (1, 4):
+                if rn == 0 and w == 4:
+                    continue
                 variants.append(dict(acs_gen=3, acs_lb=lb, acs_warps=w, acs_rn=rn))
     want = None
     for v in variants:
