@@ -445,6 +445,7 @@ int b200rx_set_pipeline_depth(b200rx_handle *h, uint32_t depth)
     }
     if (!h->ev_in) CU(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     h->depth = depth;
+    h->tn.inflight = (int)depth;
     h->call_idx = 0;
     use_lane(h, 0);
     return B200RX_OK;
@@ -501,7 +502,7 @@ namespace {
 struct OutPtrs { uint8_t *payload; uint32_t stride; uint16_t *len; uint8_t *rate; uint8_t *status; };
 
 // K1 -> K2 -> K3 for frames [off, off + n) of the batch on stream s; ev (4 events) optional.
-int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, const void *iq_dev, uint64_t iq_samples,
+int launch_range(b200rx_handle *h, const Tuning &tn, cudaStream_t s, uint32_t off, uint32_t n, const void *iq_dev, uint64_t iq_samples,
                  const uint64_t *lts1_dev, const uint32_t *avail_dev, const OutPtrs &o, const b200rx_debug *dbg,
                  cudaEvent_t *ev, const FrameRot *rot_dev = nullptr, const uint32_t *n_live_dev = nullptr)
 {
@@ -519,7 +520,7 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
     fa.bm_stride = h->max_steps;
     fa.max_steps = h->max_steps;
     fa.max_len = h->limits.max_payload_bytes;
-    fa.emit_pairs = h->tn.acs_gen == 3;
+    fa.emit_pairs = tn.acs_gen == 3;
     fa.rot = rot_dev ? rot_dev + off : nullptr;
     fa.n_live = n_live_dev;
     if (dbg) {
@@ -531,12 +532,12 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
     if (ev) CU(h, cudaEventRecord(ev[0], s));
     CU(h, launch_frontend(fa, s));
     if (ev) CU(h, cudaEventRecord(ev[1], s));
-    if (h->tn.acs_gen == 3)
+    if (tn.acs_gen == 3)
         CU(h, launch_viterbi_acs3(h->desc + off, reinterpret_cast<const uint8_t *>(h->bm + (size_t)off * S), 4 * S,
-                                  h->dec + (size_t)off * 2 * S, 2 * h->max_steps, n, false, h->tn, s));
+                                  h->dec + (size_t)off * 2 * S, 2 * h->max_steps, n, false, tn, s));
     else
         CU(h, launch_viterbi_acs(h->desc + off, h->bm + (size_t)off * S, h->max_steps, h->dec + (size_t)off * 2 * S,
-                                 2 * h->max_steps, n, h->tn, s));
+                                 2 * h->max_steps, n, tn, s));
     if (ev) CU(h, cudaEventRecord(ev[2], s));
     TracebackArgs ta{};
     ta.desc = h->desc + off;
@@ -555,7 +556,7 @@ int launch_range(b200rx_handle *h, cudaStream_t s, uint32_t off, uint32_t n, con
         ta.dbg_decoded_stride = dbg->decoded_stride;
         ta.dbg_field = dbg->header_field ? dbg->header_field + off : nullptr;
     }
-    CU(h, launch_traceback(ta, h->tn, s));
+    CU(h, launch_traceback(ta, tn, s));
     if (ev) CU(h, cudaEventRecord(ev[3], s));
     h->launches += 3;
     return B200RX_OK;
@@ -589,7 +590,7 @@ int b200rx_decode_batch_dev(b200rx_handle *h, const void *iq_dev, uint64_t iq_sa
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     cudaEvent_t *ev = call_events(h);
     const OutPtrs o{payload_out_dev, payload_stride, payload_len_dev, rate_out_dev, status_dev};
-    int rc = launch_range(h, s, 0, n_frames, iq_dev, iq_samples, lts1_index_dev, avail_dev, o, dbg, ev);
+    int rc = launch_range(h, h->tn, s, 0, n_frames, iq_dev, iq_samples, lts1_index_dev, avail_dev, o, dbg, ev);
     if (rc != B200RX_OK) return rc;
     if (ev == h->ev) h->ev_valid = true;
     if (lane) {
@@ -740,7 +741,7 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     for (uint32_t f = 1; ordered && f < n_frames; f++) ordered = lts1_index[f] >= lts1_index[f - 1];
     if (!ordered) {
         CU(h, cudaMemcpyAsync(S.d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
-        int rc = launch_range(h, s, 0, n_frames, S.d_iq, iq_samples, S.d_lts1, S.d_avail, o, nullptr, nullptr);
+        int rc = launch_range(h, h->tn, s, 0, n_frames, S.d_iq, iq_samples, S.d_lts1, S.d_avail, o, nullptr, nullptr);
         if (rc != B200RX_OK) return rc;
         if (payload_out) CU(h, cudaMemcpyAsync(payload_out, S.d_payload, pl_bytes, cudaMemcpyDeviceToHost, s));
         if (payload_len) CU(h, cudaMemcpyAsync(payload_len, S.d_len, n_frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
@@ -768,6 +769,11 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     CU(h, cudaStreamWaitEvent(h->pull_stream, ev_start, 0));
     for (int i = 0; i < 7; i++) CU(h, cudaStreamWaitEvent(h->aux_stream[i], ev_start, 0));
     uint64_t copied = 0; // samples [0, copied) are on their way
+    // The link is the bottleneck here; what the kernels owe it is a short tail behind the last chunk's samples.  A chunk of
+    // a few hundred frames is decoded fastest by the generation-2 ACS kernel with 16 lanes per frame (0.7 ms for 12 096
+    // steps however few frames; generation 3 needs 1.4-1.7 ms for a lone chunk and wins only once the GPU is full).
+    Tuning tn_chunk = h->tn;
+    if (h->tn.acs_gen == 3 && CH <= 2048) tn_chunk.acs_gen = 2;
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t f0 = bound[c], f1 = bound[c + 1];
         uint64_t hi = 0;
@@ -793,7 +799,7 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
         CU(h, cudaEventRecord(ev_in, in_stream));
         cudaStream_t cs = (c & 7) ? h->aux_stream[(c & 7) - 1] : s;
         CU(h, cudaStreamWaitEvent(cs, ev_in, 0));
-        int rc = launch_range(h, cs, f0, f1 - f0, S.d_iq, iq_samples, S.d_lts1, S.d_avail, o, nullptr, nullptr);
+        int rc = launch_range(h, tn_chunk, cs, f0, f1 - f0, S.d_iq, iq_samples, S.d_lts1, S.d_avail, o, nullptr, nullptr);
         if (rc != B200RX_OK) return rc;
         CU(h, cudaEventRecord(ev_out, cs));
         CU(h, cudaStreamWaitEvent(h->d2h_stream, ev_out, 0));
@@ -956,7 +962,7 @@ int b200rx_receive_dev(b200rx_handle *h, const void *iq_dev, uint64_t n_samples,
     const b200rx_handle::SyncScratch &y = h->sy[li];
     cudaEvent_t *ev = call_events(h);
     const OutPtrs o{payload_out_dev, payload_stride, payload_len_dev, rate_out_dev, status_dev};
-    rc = launch_range(h, s, 0, mf, iq_dev, n_samples, y.lts1, y.avail, o, nullptr, ev, y.rot, &y.summary->n_frames);
+    rc = launch_range(h, h->tn, s, 0, mf, iq_dev, n_samples, y.lts1, y.avail, o, nullptr, ev, y.rot, &y.summary->n_frames);
     if (rc != B200RX_OK) return rc;
     if (ev == h->ev) h->ev_valid = true;
     if (lts1_out_dev) CU(h, cudaMemcpyAsync(lts1_out_dev, y.lts1, (size_t)mf * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));

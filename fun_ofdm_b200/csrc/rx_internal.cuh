@@ -193,6 +193,8 @@ struct Tuning {
     int h2d_chunk = 1024;   // b200rx_submit_batch: frames per pipelined chunk, and the size the last chunks shrink to
     int h2d_chunk_min = 256;
     int pull_mode = -1;     // host-buffer ingest: 0 DMA copy, 1 GPU pull when the buffer is pinned, 2 alternate, -1 by format
+    int inflight = 1;       // batches the caller keeps in flight on this handle (pipeline depth): the ACS launcher sizes its
+                            // warps for the GPU being shared, not for one batch alone
     int fe_split = 1;       // front end: 1 = header kernel + one warp per OFDM symbol over all frames, 0 = one CTA per frame
 };
 

@@ -657,7 +657,8 @@ cudaError_t launch_viterbi_acs3(const FrameDesc *desc, const uint8_t *soft, uint
     // Lanes per frame pair: 4 (16 frames per warp) once the batch gives every scheduler a warp that way, else 8.
     const uint32_t sched = 4u * (uint32_t)tn.sm_count;
     // (bench.py, config 2, 12 batches in flight: LB = 2 with 4-warp CTAs 0.797 ms per step, 2-warp CTAs 0.82-0.84, LB = 3 0.844)
-    int lb = (n_frames >= 16u * sched * 3u / 4u) ? 2 : 3;
+    const uint64_t eff = (uint64_t)n_frames * (uint64_t)(tn.inflight > 1 ? tn.inflight : 1);
+    int lb = (eff >= 16u * sched * 3u / 4u) ? 2 : 3;
     if (tn.acs_lb >= 2 && tn.acs_lb <= 3) lb = tn.acs_lb;
     int cta_warps = tn.acs_warps;
     if (cta_warps != 1 && cta_warps != 2 && cta_warps != 4) cta_warps = 4;

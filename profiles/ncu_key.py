@@ -31,8 +31,9 @@ def main():
     out = {"source": sys.argv[1].split("/")[-1], "kernels": {}}
     for r in body:
         name = r[idx["Kernel Name"]]
-        short = "frontend_kernel" if "frontend" in name else "traceback_kernel" if "traceback" in name else \
-            "viterbi_acs2_kernel" if "viterbi_acs2" in name else name
+        short = name.split("(")[0].split("<")[0].split("::")[-1].split(" ")[-1]  # bare function name
+        if short in out["kernels"]:
+            continue  # first launch of each kernel
         k = {"full_name": name}
         for key, label in KEYS.items():
             if key in idx and r[idx[key]] != "":
