@@ -34,6 +34,7 @@ struct b200rx_handle {
     uint32_t *bm = nullptr;  // front end -> ACS: metric words (4 B per step) or soft-symbol pairs (2 B per step)
     uint32_t *dec = nullptr; // survivor words: 2 per trellis step per frame
     unsigned long long *counters = nullptr; // 8 words (5 used)
+    double2 *hinv = nullptr; // split front end: inverse channel per frame, header pass -> data kernel
     Tuning tn;
 
     // staging of the host-buffer entry points (grow-only).  b200rx_submit_batch keeps up to B200RX_MAX_INFLIGHT calls in
@@ -47,6 +48,7 @@ struct b200rx_handle {
         uint8_t *d_rate = nullptr;
         uint8_t *d_status = nullptr;
         FrameDesc *desc = nullptr; uint32_t *bm = nullptr; uint32_t *dec = nullptr; unsigned long long *counters = nullptr;
+        double2 *hinv = nullptr;
         std::vector<cudaEvent_t> pipe_ev; // 2 per chunk (samples landed, results ready) + 1
         cudaEvent_t done = nullptr;
         bool busy = false;
@@ -59,6 +61,7 @@ struct b200rx_handle {
     // so that batch j+1 starts while batch j is still in its Viterbi kernel (b200rx_set_pipeline_depth)
     struct Lane {
         FrameDesc *desc = nullptr; uint32_t *bm = nullptr; uint32_t *dec = nullptr; unsigned long long *counters = nullptr;
+        double2 *hinv = nullptr;
         cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; bool used = false;
     };
     Lane lanes[B200RX_MAX_PIPELINE_DEPTH];
@@ -120,6 +123,7 @@ inline cudaEvent_t *call_events(b200rx_handle *h)
 inline void use_lane(b200rx_handle *h, int i)
 {
     h->desc = h->lanes[i].desc; h->bm = h->lanes[i].bm; h->dec = h->lanes[i].dec; h->counters = h->lanes[i].counters;
+    h->hinv = h->lanes[i].hinv;
 }
 
 #define CU(h, call)                                                         \
@@ -145,22 +149,23 @@ std::mutex g_device_init_mutex;
 bool g_device_ready[64] = {false}; // constant tables uploaded and function attributes set, per device
 
 // one scratch set {desc, bm, dec, counters}: all four or none
-struct ScratchPtrs { FrameDesc *desc; uint32_t *bm; uint32_t *dec; unsigned long long *counters; };
+struct ScratchPtrs { FrameDesc *desc; uint32_t *bm; uint32_t *dec; unsigned long long *counters; double2 *hinv; };
 
 void free_scratch(ScratchPtrs &p)
 {
-    cudaFree(p.desc); cudaFree(p.bm); cudaFree(p.dec); cudaFree(p.counters);
-    p.desc = nullptr; p.bm = nullptr; p.dec = nullptr; p.counters = nullptr;
+    cudaFree(p.desc); cudaFree(p.bm); cudaFree(p.dec); cudaFree(p.counters); cudaFree(p.hinv);
+    p.desc = nullptr; p.bm = nullptr; p.dec = nullptr; p.counters = nullptr; p.hinv = nullptr;
 }
 
 cudaError_t alloc_scratch(const b200rx_handle *h, ScratchPtrs &p)
 {
     const size_t nf = h->limits.max_frames;
-    p.desc = nullptr; p.bm = nullptr; p.dec = nullptr; p.counters = nullptr;
+    p.desc = nullptr; p.bm = nullptr; p.dec = nullptr; p.counters = nullptr; p.hinv = nullptr;
     cudaError_t e = cudaMalloc((void **)&p.desc, nf * sizeof(FrameDesc));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p.bm, nf * (size_t)h->max_steps * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p.dec, nf * (size_t)h->max_steps * 2 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p.counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p.hinv, nf * 64 * sizeof(double2));
     if (e != cudaSuccess) {
         free_scratch(p);
         (void)cudaGetLastError();
@@ -303,7 +308,9 @@ int b200rx_create(int device, const b200rx_limits *limits, b200rx_handle **out)
         ScratchPtrs sp;
         e = alloc_scratch(h, sp);
         h->lanes[0].desc = sp.desc; h->lanes[0].bm = sp.bm; h->lanes[0].dec = sp.dec; h->lanes[0].counters = sp.counters;
+        h->lanes[0].hinv = sp.hinv;
         h->hs[0].desc = sp.desc; h->hs[0].bm = sp.bm; h->hs[0].dec = sp.dec; h->hs[0].counters = sp.counters;
+        h->hs[0].hinv = sp.hinv;
         use_lane(h, 0);
     }
     A((void **)&h->hs[0].d_lts1, nf * sizeof(uint64_t));
@@ -332,7 +339,7 @@ int b200rx_destroy(b200rx_handle *h)
         b200rx_handle::Lane &l = h->lanes[i];
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
         if (l.done) cudaEventDestroy(l.done);
-        cudaFree(l.desc); cudaFree(l.bm); cudaFree(l.dec); cudaFree(l.counters); // set 0 included (shared with host slot 0)
+        cudaFree(l.desc); cudaFree(l.bm); cudaFree(l.dec); cudaFree(l.counters); cudaFree(l.hinv); // set 0 included (shared with host slot 0)
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (auto &y : h->sy) {
@@ -346,7 +353,7 @@ int b200rx_destroy(b200rx_handle *h)
         if (S.done) { cudaEventSynchronize(S.done); cudaEventDestroy(S.done); }
         cudaFree(S.d_iq); cudaFree(S.d_lts1); cudaFree(S.d_avail); cudaFree(S.d_payload);
         cudaFree(S.d_len); cudaFree(S.d_rate); cudaFree(S.d_status);
-        if (i > 0) { cudaFree(S.desc); cudaFree(S.bm); cudaFree(S.dec); cudaFree(S.counters); }
+        if (i > 0) { cudaFree(S.desc); cudaFree(S.bm); cudaFree(S.dec); cudaFree(S.counters); cudaFree(S.hinv); }
         for (cudaEvent_t e : S.pipe_ev) if (e) cudaEventDestroy(e);
     }
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -440,7 +447,7 @@ int b200rx_set_pipeline_depth(b200rx_handle *h, uint32_t depth)
             ScratchPtrs sp;
             cudaError_t e = alloc_scratch(h, sp);
             if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_set_pipeline_depth: scratch for an extra lane", e);
-            l.desc = sp.desc; l.bm = sp.bm; l.dec = sp.dec; l.counters = sp.counters;
+            l.desc = sp.desc; l.bm = sp.bm; l.dec = sp.dec; l.counters = sp.counters; l.hinv = sp.hinv;
         }
     }
     if (!h->ev_in) CU(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
@@ -530,7 +537,15 @@ int launch_range(b200rx_handle *h, const Tuning &tn, cudaStream_t s, uint32_t of
         fa.dbg_depunct_stride = dbg->depunct_stride;
     }
     if (ev) CU(h, cudaEventRecord(ev[0], s));
-    CU(h, launch_frontend(fa, s));
+    if (tn.fe_split && tn.acs_gen == 3) { // header pass (descriptor + H^-1 per frame), then the data symbols
+        fa.header_only = 2;
+        fa.hinv_out = h->hinv + (size_t)off * 64;
+        CU(h, launch_frontend(fa, s));
+        CU(h, launch_frontend_data(fa, s));
+        h->launches++;
+    } else {
+        CU(h, launch_frontend(fa, s));
+    }
     if (ev) CU(h, cudaEventRecord(ev[1], s));
     if (tn.acs_gen == 3)
         CU(h, launch_viterbi_acs3(h->desc + off, reinterpret_cast<const uint8_t *>(h->bm + (size_t)off * S), 4 * S,
@@ -627,7 +642,7 @@ int ensure_host_slot(b200rx_handle *h, int k)
         (void)cudaGetLastError();
         return fail(h, B200RX_E_NOMEM, "b200rx_submit_batch: scratch for another call in flight", e);
     }
-    S.desc = sp.desc; S.bm = sp.bm; S.dec = sp.dec; S.counters = sp.counters;
+    S.desc = sp.desc; S.bm = sp.bm; S.dec = sp.dec; S.counters = sp.counters; S.hinv = sp.hinv;
     S.d_lts1 = d_lts1; S.d_avail = d_avail; S.d_len = d_len; S.d_rate = d_rate; S.d_status = d_status;
     return B200RX_OK;
 }
@@ -688,7 +703,7 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     { int rcw = wait_slot(h, S); if (rcw != B200RX_OK) return rcw; }
     { int rce = ensure_host_slot(h, k); if (rce != B200RX_OK) return rce; }
     cudaStream_t s = h->stream;
-    h->desc = S.desc; h->bm = S.bm; h->dec = S.dec; h->counters = S.counters;
+    h->desc = S.desc; h->bm = S.bm; h->dec = S.dec; h->counters = S.counters; h->hinv = S.hinv;
 
     const size_t bps = sample_bytes(h->fmt);
     const size_t iq_bytes = (size_t)iq_samples * bps;

@@ -36,6 +36,14 @@ constexpr int ERASURE_AT = 288;
 // re-inserted erasure (value 127).  Filled by upload_frontend_tables from step_index_pair() below.
 __constant__ uint32_t c_step_idx[11][216];
 
+// Inverse of c_step_idx for the data kernel: soft byte i (demodulator order) of an OFDM symbol -> its byte offset 2 * t + slot
+// in the symbol's run of depunctured soft-symbol pairs; the offsets no soft byte maps to are the re-inserted erasures.
+__constant__ uint16_t c_scatter[11][288];
+// QAM<N>::decode (qam.h:110-125) of one axis as a table: soft bits of pt = clamp(u, -320, 320), byte i = bit i, for
+// N = 1, 2, 3 (beyond +-320 every bit has reached its final value 0 or 255).
+constexpr int SOFT_TAB_HALF = 320, SOFT_TAB_N = 2 * SOFT_TAB_HALF + 1;
+__constant__ uint32_t c_soft_tab[3][SOFT_TAB_N];
+
 __constant__ double2 c_twiddle[64];  // exp(-2 pi i k / 64)
 __constant__ int8_t c_polarity[127]; // pilot polarity sequence (phase_tracker.cpp:23-32)
 
@@ -274,7 +282,10 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(
         }
     }
     __syncthreads();
-    if (tid < 64) s_hinv[tid] = cadd(s_xs[0][tid], s_xs[1][tid]);
+    if (tid < 64) {
+        s_hinv[tid] = cadd(s_xs[0][tid], s_xs[1][tid]);
+        if (a.hinv_out) a.hinv_out[(size_t)frame * 64 + tid] = s_hinv[tid]; // for data_kernel (split front end)
+    }
     __syncthreads();
 
     // ---- SIGNAL: ppdu.cpp:168-218 ----
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(
                 s_desc.rate = (uint8_t)rate;
                 s_desc.length = (uint16_t)len;
                 if (len > a.max_len || steps > a.max_steps) s_desc.status = B200RX_ST_TOO_LONG;
-                else if (!a.header_only && (uint64_t)avail < 128ull + 80ull * (1ull + nsym)) s_desc.status = B200RX_ST_TRUNCATED;
+                else if (a.header_only != 1 && (uint64_t)avail < 128ull + 80ull * (1ull + nsym)) s_desc.status = B200RX_ST_TRUNCATED;
                 else {
                     s_desc.status = B200RX_ST_OK;
                     s_desc.n_steps = steps;
@@ -348,20 +359,294 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Data symbols of the split front end (Tuning::fe_split): everything frontend_kernel does after SIGNAL, for frames whose
+// descriptor and inverse channel the header pass (frontend_kernel, header_only = 2) has written.
+//
+// ncu on frontend_kernel (profiles/r01_v9_ncu_full.md): 559 warp instructions per OFDM symbol, 2.0 TB/s - bound by
+// instruction issue, not by HBM.  Here a symbol costs about a quarter of that:
+//   * 8 lanes per symbol, 8 points per lane, four symbols per warp: the 64-point DFT is 8-point DFTs in registers
+//     (constant twiddles, half of them trivial), one transposition through shared memory, 8-point DFTs again -
+//     no shuffles (the two-points-per-lane radix-2 version spends 40 SHFL + 5 twiddle multiplies per lane per symbol);
+//   * equalise, pilots, derotation and demapping run on the registers the DFT left behind (lane r holds bins r + 8 k);
+//   * QAM<N>::decode is a table look-up on the truncated integer (qam.h:112), built from the same recurrence;
+//   * deinterleave + depuncture is a scatter: every soft byte is stored once, at the place it has in the symbol's run of
+//     (s0, s1) pairs (c_scatter), into a tile whose erasure bytes were set to 127 once; the tile leaves with 8-byte
+//     coalesced stores.
+// One CTA (4 warps) per frame; no barrier after the setup.
+// ------------------------------------------------------------------------------------------------
+constexpr int DK_WARPS = 4;
+constexpr int DK_TR_STRIDE = 9;      // double2 per transposition row (8 + 1: 16-byte accesses of 8 lanes hit 8 bank groups)
+constexpr int DK_PAIR_BYTES = 432;   // 2 * max dbps
+
+// In-place 8-point forward DFT, natural order in and out.
+__device__ __forceinline__ void dft8(double2 (&x)[8])
+{
+    const double h = 0.70710678118654752440; // 1 / sqrt(2)
+    const double2 a0 = cadd(x[0], x[4]), b0 = csub(x[0], x[4]);
+    const double2 a1 = cadd(x[1], x[5]), t1 = csub(x[1], x[5]);
+    const double2 a2 = cadd(x[2], x[6]), t2 = csub(x[2], x[6]);
+    const double2 a3 = cadd(x[3], x[7]), t3 = csub(x[3], x[7]);
+    const double2 b1 = make_double2((t1.x + t1.y) * h, (t1.y - t1.x) * h);   // * (1 - i) / sqrt 2
+    const double2 b2 = make_double2(t2.y, -t2.x);                             // * -i
+    const double2 b3 = make_double2((t3.y - t3.x) * h, (-t3.x - t3.y) * h);  // * (-1 - i) / sqrt 2
+    {
+        const double2 s0 = cadd(a0, a2), d0 = csub(a0, a2), s1 = cadd(a1, a3), u = csub(a1, a3);
+        const double2 d1 = make_double2(u.y, -u.x);
+        x[0] = cadd(s0, s1); x[4] = csub(s0, s1); x[2] = cadd(d0, d1); x[6] = csub(d0, d1);
+    }
+    {
+        const double2 s0 = cadd(b0, b2), d0 = csub(b0, b2), s1 = cadd(b1, b3), u = csub(b1, b3);
+        const double2 d1 = make_double2(u.y, -u.x);
+        x[1] = cadd(s0, s1); x[5] = csub(s0, s1); x[3] = cadd(d0, d1); x[7] = csub(d0, d1);
+    }
+}
+
+struct DataArgs {
+    const void *iq;
+    double scale;
+    uint64_t iq_samples;
+    const uint64_t *lts1;
+    uint32_t n_frames;
+    const FrameDesc *desc;
+    const double2 *hinv;     // [n_frames][64], shifted order
+    uint8_t *pairs;          // [n_frames][pair_stride] bytes: (s0, s1) per trellis step
+    uint64_t pair_stride;
+    const FrameRot *rot;
+    double2 *dbg_eq;
+    uint32_t dbg_eq_vectors;
+    uint8_t *dbg_depunct;
+    uint32_t dbg_depunct_stride;
+};
+
+// The symbol loop of data_kernel for one modulation (BPSC soft bits per carrier): specialised so that the per-carrier
+// work has no branches.
+template <bool ROT, int FMT, bool DBG, int BPSC>
+__device__ __forceinline__ void data_symbols(const DataArgs &a, int frame, const FrameDesc &d, const Window &win, const RotCtx &rc,
+                                             double2 *tr_row, const double2 *tr_col, double2 *pil, const double2 *hinv_r,
+                                             const double2 *tw_r, const uint32_t *soft_tab, const uint16_t *scatter,
+                                             uint8_t *tile, int lane, int warp)
+{
+    const int q = lane >> 3, r = lane & 7;
+    const int dbps = rate_row(d.rate).dbps;
+    const uint32_t nsym = d.n_steps / (uint32_t)dbps;
+    const double scale = demap_scale(BPSC);
+    // which of this lane's bins r + 8 k2 carry data, and where the carrier's soft bytes go in the symbol's run of pairs
+    const uint16_t *sc[8];
+    bool is_data[8];
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        const int s = (r + 8 * k2 + 32) & 63; // shifted index: subcarrier s - 32
+        is_data[k2] = s >= 6 && s <= 58 && s != 11 && s != 25 && s != 32 && s != 39 && s != 53;
+        const int c = s - 6 - (s > 11) - (s > 25) - (s > 32) - (s > 39) - (s > 53);
+        sc[k2] = scatter + (is_data[k2] ? c * BPSC : 0);
+    }
+    // pilot of this lane (odd lanes): pilot number pp (phase_tracker.cpp:37-43: bins 11, 25, 39, 53 = r 3, 1, 7, 5)
+    const int pp = r == 3 ? 0 : (r == 1 ? 1 : (r == 7 ? 2 : 3));
+    const double psign = (pp == 3) ? -0.25 : 0.25; // sign_p / 4: an exact scaling, so (x * ref) / 4 == x * (ref / 4)
+    uint8_t *st = tile + q * 2 * dbps;
+    uint8_t *out = a.pairs + (size_t)frame * a.pair_stride;
+
+    for (uint32_t g = warp; 4 * g < nsym; g += DK_WARPS) {
+        const uint32_t sym = 4 * g + q;
+        const bool live = sym < nsym;
+        const int off = 128 + 80 * (int)(live ? sym + 1 : 1) + 16 + r; // dead lanes of the last group re-read symbol 0
+        double2 x[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) x[n1] = fetch<ROT, FMT>(win, off + 8 * n1, rc);
+        // X[k1 + 8 k2] = sum_r W64^(r k1) W8^(r k2) [ sum_n1 x[8 n1 + r] W8^(n1 k1) ]
+        dft8(x);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) x[k1] = cmul(x[k1], tw_r[8 * k1]);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) tr_row[k1] = x[k1];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = tr_col[j * DK_TR_STRIDE];
+        dft8(x); // x[k2] = X[r + 8 k2]
+
+        // channel_est.cpp:77-81: out = H^-1 * in   (hinv_r[k2] = H^-1 of bin r + 8 k2)
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) x[k2] = cmul(hinv_r[8 * k2], x[k2]);
+        // phase_tracker.cpp:83-92: e = sum_p rec_p * (sign_p * POLARITY[n % 127]) / 4, summed as (e0 + e1) + (e2 + e3)
+        {
+            const double ref4 = (double)c_polarity[(live ? sym + 1 : 1) % 127] * psign;
+            const double2 pv = r == 3 ? x[5] : (r == 1 ? x[7] : (r == 7 ? x[0] : x[2]));
+            if (r & 1) pil[pp] = make_double2(pv.x * ref4, pv.y * ref4);
+        }
+        __syncwarp();
+        const double2 e = cadd(cadd(pil[0], pil[1]), cadd(pil[2], pil[3]));
+        // phase_tracker.cpp:92-98 rotates by exp(-i arg(e)) = conj(e) / |e|
+        const double m2 = e.x * e.x + e.y * e.y;
+        const double inv = rsqrt(m2);
+        const double2 rot = (m2 > 0.0) ? make_double2(e.x * inv, -e.y * inv) : make_double2(1.0, 0.0);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            const double2 y = cmul(x[k2], rot);
+            const bool on = is_data[k2] && live;
+            if constexpr (DBG) {
+                if (a.dbg_eq && on && sym + 1 < a.dbg_eq_vectors)
+                    a.dbg_eq[((size_t)frame * a.dbg_eq_vectors + sym + 1) * 48 + (sc[k2] - scatter) / BPSC] = y;
+            }
+            // modulator.cpp:118-160: real axis first, then imaginary (BPSK: real only); qam.h:112 truncates toward zero
+            const int ur = min(max(__double2int_rz(y.x * scale), -SOFT_TAB_HALF), SOFT_TAB_HALF);
+            const uint32_t br = soft_tab[ur];
+            const uint16_t *p = sc[k2];
+            if constexpr (BPSC == 1) {
+                if (on) st[p[0]] = (uint8_t)br;
+            } else {
+                const int ui = min(max(__double2int_rz(y.y * scale), -SOFT_TAB_HALF), SOFT_TAB_HALF);
+                const uint32_t bi = soft_tab[ui];
+                if constexpr (BPSC == 2) {
+                    if (on) { st[p[0]] = (uint8_t)br; st[p[1]] = (uint8_t)bi; }
+                } else if constexpr (BPSC == 4) {
+                    if (on) {
+                        st[p[0]] = (uint8_t)br; st[p[1]] = (uint8_t)(br >> 8);
+                        st[p[2]] = (uint8_t)bi; st[p[3]] = (uint8_t)(bi >> 8);
+                    }
+                } else {
+                    if (on) {
+                        st[p[0]] = (uint8_t)br; st[p[1]] = (uint8_t)(br >> 8); st[p[2]] = (uint8_t)(br >> 16);
+                        st[p[3]] = (uint8_t)bi; st[p[4]] = (uint8_t)(bi >> 8); st[p[5]] = (uint8_t)(bi >> 16);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // the group's run of pairs: symbols 4g .. 4g+3 are contiguous in the tile and in the frame's pair buffer
+        const uint32_t cnt = min(4u, nsym - 4 * g);
+        const uint32_t n8 = cnt * 2 * dbps / 8;
+        const size_t gofs = (size_t)4 * g * 2 * dbps;
+        for (uint32_t i = lane; i < n8; i += 32)
+            reinterpret_cast<uint2 *>(out + gofs)[i] = reinterpret_cast<const uint2 *>(tile)[i];
+        if constexpr (DBG) {
+            if (a.dbg_depunct)
+                for (uint32_t i = lane; i < cnt * 2 * dbps; i += 32)
+                    if (gofs + i < a.dbg_depunct_stride) a.dbg_depunct[(size_t)frame * a.dbg_depunct_stride + gofs + i] = tile[i];
+        }
+        __syncwarp();
+    }
+}
+
+template <bool ROT, int FMT, bool DBG>
+__global__ void __launch_bounds__(DK_WARPS * 32) data_kernel(DataArgs a)
+{
+    __shared__ double2 s_hinv[64];      // [k2][r] = H^-1 of DFT bin r + 8 k2 (natural DFT order): lane r reads [k2][r], conflict-free
+    __shared__ double2 s_tw[8][8];      // [k1][r] = W64^(r k1)
+    __shared__ __align__(16) double2 s_tr[DK_WARPS][4][8][DK_TR_STRIDE];
+    __shared__ __align__(16) double2 s_pil[DK_WARPS][4][4];
+    __shared__ __align__(16) uint8_t s_pairs[DK_WARPS][4 * DK_PAIR_BYTES];
+    __shared__ uint16_t s_scatter[288];
+    __shared__ uint32_t s_soft[SOFT_TAB_N];
+
+    const int frame = blockIdx.x;
+    const FrameDesc d = a.desc[frame];
+    if (d.status != B200RX_ST_OK || d.n_steps == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = lane >> 3, r = lane & 7;
+    const int bpsc = rate_row(d.rate).bpsc;
+    const int tab = bpsc <= 2 ? 0 : (bpsc == 4 ? 1 : 2);
+
+    if (tid < 64) {
+        s_hinv[tid] = a.hinv[(size_t)frame * 64 + ((tid + 32) & 63)]; // a.hinv is in the reference's shifted order
+        s_tw[tid >> 3][tid & 7] = c_twiddle[((tid >> 3) * (tid & 7)) & 63];
+    }
+    for (int i = tid; i < 288; i += DK_WARPS * 32) s_scatter[i] = c_scatter[d.rate][i];
+    for (int i = tid; i < SOFT_TAB_N; i += DK_WARPS * 32) s_soft[i] = c_soft_tab[tab][i];
+    for (int i = tid; i < DK_WARPS * 4 * DK_PAIR_BYTES / 4; i += DK_WARPS * 32)
+        reinterpret_cast<uint32_t *>(&s_pairs[0][0])[i] = 0x7F7F7F7Fu; // erasures (puncturer.cpp:98): data bytes are overwritten per symbol
+    __syncthreads();
+
+    const Window win{a.iq, a.lts1[frame], a.scale};
+    RotCtx rc{};
+    if constexpr (ROT) {
+        const FrameRot fr = a.rot[frame];
+        rc.rn = fr.rot_new;
+        rc.ro = fr.rot_old;
+        rc.from = (int64_t)fr.from - (int64_t)win.p;
+    }
+    double2 *tr_row = &s_tr[warp][q][r][0];
+    const double2 *tr_col = &s_tr[warp][q][0][r];
+    double2 *pil = &s_pil[warp][q][0];
+    const double2 *hinv_r = &s_hinv[r];
+    const double2 *tw_r = &s_tw[0][r];
+    const uint32_t *soft_tab = s_soft + SOFT_TAB_HALF;
+    uint8_t *tile = &s_pairs[warp][0];
+    switch (bpsc) {
+        case 1: data_symbols<ROT, FMT, DBG, 1>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+        case 2: data_symbols<ROT, FMT, DBG, 2>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+        case 4: data_symbols<ROT, FMT, DBG, 4>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+        default: data_symbols<ROT, FMT, DBG, 6>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+    }
+}
+
 } // namespace
 
 cudaError_t upload_frontend_tables(const double2 *tw, const int8_t *pol)
 {
     static uint32_t idx[11][216];
+    static uint16_t scatter[11][288];
     for (int r = 0; r < 11; r++) {
         const RateRow rr = rate_row(r);
-        for (int t = 0; t < 216; t++) idx[r][t] = t < rr.dbps ? step_index_pair(rr.punc, t) : (ERASURE_AT | (ERASURE_AT << 16));
+        for (int i = 0; i < 288; i++) scatter[r][i] = 0;
+        for (int t = 0; t < 216; t++) {
+            idx[r][t] = t < rr.dbps ? step_index_pair(rr.punc, t) : (ERASURE_AT | (ERASURE_AT << 16));
+            if (t < rr.dbps) {
+                const uint32_t i0 = idx[r][t] & 0xFFFFu, i1 = idx[r][t] >> 16;
+                if (i0 != ERASURE_AT) scatter[r][i0] = (uint16_t)(2 * t);
+                if (i1 != ERASURE_AT) scatter[r][i1] = (uint16_t)(2 * t + 1);
+            }
+        }
     }
+    // QAM<N>::decode (qam.h:110-125) of one axis on the truncated integer pt (see qam_decode_axis)
+    static uint32_t soft[3][SOFT_TAB_N];
+    for (int nb = 1; nb <= 3; nb++)
+        for (int i = 0; i < SOFT_TAB_N; i++) {
+            int u = i - SOFT_TAB_HALF, amp = 128;
+            uint32_t w = 0;
+            for (int b = 0; b < nb; b++) {
+                const int v = u + 128;
+                w |= (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)) << (8 * b);
+                u = amp - (u < 0 ? -u : u);
+                amp >>= 1;
+            }
+            soft[nb - 1][i] = w;
+        }
     cudaError_t e = cudaMemcpyToSymbol(c_step_idx, idx, sizeof(idx));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_scatter, scatter, sizeof(scatter));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_soft_tab, soft, sizeof(soft));
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_twiddle, tw, sizeof(double2) * 64);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_polarity, pol, 127);
+}
+
+// Data symbols of the split front end; a.desc / a.hinv_out were written by launch_frontend(header_only = 2).
+cudaError_t launch_frontend_data(const FrontendArgs &a, cudaStream_t s)
+{
+    if (a.n_frames == 0) return cudaSuccess;
+    DataArgs d{};
+    d.iq = a.iq; d.scale = a.scale; d.iq_samples = a.iq_samples; d.lts1 = a.lts1; d.n_frames = a.n_frames; d.desc = a.desc;
+    d.hinv = a.hinv_out; d.pairs = reinterpret_cast<uint8_t *>(a.bm); d.pair_stride = (uint64_t)a.bm_stride * 4; d.rot = a.rot;
+    d.dbg_eq = a.dbg_eq; d.dbg_eq_vectors = a.dbg_eq_vectors; d.dbg_depunct = a.dbg_depunct; d.dbg_depunct_stride = a.dbg_depunct_stride;
+    const dim3 grid(a.n_frames), block(DK_WARPS * 32);
+    const bool dbg = a.dbg_eq != nullptr || a.dbg_depunct != nullptr;
+#define DK_LAUNCH(ROTV, FMTV) do { if (dbg) data_kernel<ROTV, FMTV, true><<<grid, block, 0, s>>>(d); \
+                                   else data_kernel<ROTV, FMTV, false><<<grid, block, 0, s>>>(d); } while (0)
+    switch (a.fmt * 2 + (a.rot ? 1 : 0)) {
+        case FMT_FC64 * 2: DK_LAUNCH(false, FMT_FC64); break;
+        case FMT_FC64 * 2 + 1: DK_LAUNCH(true, FMT_FC64); break;
+        case FMT_FC32 * 2: DK_LAUNCH(false, FMT_FC32); break;
+        case FMT_FC32 * 2 + 1: DK_LAUNCH(true, FMT_FC32); break;
+        case FMT_SC16 * 2: DK_LAUNCH(false, FMT_SC16); break;
+        case FMT_SC16 * 2 + 1: DK_LAUNCH(true, FMT_SC16); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef DK_LAUNCH
+    return cudaGetLastError();
 }
 
 cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s)

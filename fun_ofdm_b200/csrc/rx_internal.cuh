@@ -213,7 +213,9 @@ struct FrontendArgs {
     int emit_pairs;          // 1: the same buffer receives soft-symbol pairs, 2 bytes per trellis step (ACS generation 3)
     uint32_t max_steps;
     uint32_t max_len;
-    int header_only;         // 1: stop after the SIGNAL symbol (descriptor only, no branch metrics)
+    int header_only;         // 1: stop after the SIGNAL symbol (descriptor only, no length check against `avail`);
+                             // 2: header pass of the split front end (full status logic, exports H^-1 to hinv_out)
+    double2 *hinv_out;       // [n_frames][64] inverse channel of each frame (shifted order), or null
     const FrameRot *rot;     // per frame, or null: samples are used as they are
     const uint32_t *n_live;  // device count of valid frames (slots beyond it become B200RX_ST_NO_FRAME), or null
     // taps (may be null)
@@ -224,6 +226,7 @@ struct FrontendArgs {
 };
 
 cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s);
+cudaError_t launch_frontend_data(const FrontendArgs &a, cudaStream_t s); // data symbols after launch_frontend(header_only = 2)
 
 cudaError_t launch_bm_from_symbols(const uint8_t *symbols, uint64_t symbols_stride, const uint32_t *data_bits,
                                    uint32_t max_data_bits, uint32_t n_frames, FrameDesc *desc, uint32_t *bm,
