@@ -93,6 +93,24 @@ struct b200rx_handle {
     int64_t *d_origins[B200RX_MAX_PIPELINE_DEPTH] = {};
     uint32_t d_origins_cap[B200RX_MAX_PIPELINE_DEPTH] = {};
 
+    // two-phase passes (b200rx_pass_*): per lane a stream, sample / output staging and the host-mapped frame list
+    struct PassLane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        uint8_t *d_iq = nullptr; size_t d_iq_cap = 0;          // bytes, samples in the handle's format
+        uint8_t *d_payload = nullptr; size_t d_payload_cap = 0;
+        uint8_t *d_status = nullptr, *d_select = nullptr;      // [max_frames]
+        uint8_t *h_list = nullptr, *h_list_dev = nullptr;      // pinned + mapped: SyncSummary, then b200rx_pass_frame[max_frames]
+        uint8_t *h_select = nullptr;                           // pinned [max_frames]
+        uint64_t fill = 0;                                     // samples staged so far
+        uint32_t n_frames = 0;
+        bool scanned = false, busy = false;
+        uint64_t ticket = 0;
+    };
+    PassLane pl[B200RX_MAX_PIPELINE_DEPTH];
+    int pass_lane = -1;
+    uint64_t pass_count = 0, pass_next_ticket = 1;
+
     // format of every `iq` argument (b200rx_set_sample_format)
     int fmt = FMT_FC64;
     double scale = 1.0;
@@ -356,6 +374,13 @@ int b200rx_destroy(b200rx_handle *h)
         if (i > 0) { cudaFree(S.desc); cudaFree(S.bm); cudaFree(S.dec); cudaFree(S.counters); cudaFree(S.hinv); }
         for (cudaEvent_t e : S.pipe_ev) if (e) cudaEventDestroy(e);
     }
+    for (auto &P : h->pl) {
+        if (P.stream) { cudaStreamSynchronize(P.stream); cudaStreamDestroy(P.stream); }
+        if (P.done) cudaEventDestroy(P.done);
+        cudaFree(P.d_iq); cudaFree(P.d_payload); cudaFree(P.d_status); cudaFree(P.d_select);
+        if (P.h_list) cudaFreeHost(P.h_list);
+        if (P.h_select) cudaFreeHost(P.h_select);
+    }
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -428,6 +453,11 @@ int b200rx_synchronize(b200rx_handle *h)
             CU(h, cudaEventSynchronize(S.done));
             S.busy = false;
         }
+    for (auto &P : h->pl)
+        if (P.stream) {
+            CU(h, cudaStreamSynchronize(P.stream));
+            P.busy = false;
+        }
     CU(h, cudaStreamSynchronize(h->stream));
     return B200RX_OK;
 }
@@ -464,7 +494,14 @@ int b200rx_join_on(b200rx_handle *h, uint32_t calls_back, void *cuda_stream)
 {
     if (!h) return B200RX_E_ARG;
     cudaStream_t target = (cudaStream_t)cuda_stream;
-    if (h->depth <= 1) return B200RX_OK; // everything already runs in order on the caller's stream
+    if (h->depth <= 1) { // everything runs in order on the handle's stream: another stream waits for what is queued there
+        if (target == h->stream) return B200RX_OK;
+        CU(h, cudaSetDevice(h->device));
+        if (!h->ev_in) CU(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        CU(h, cudaEventRecord(h->ev_in, h->stream));
+        CU(h, cudaStreamWaitEvent(target, h->ev_in, 0));
+        return B200RX_OK;
+    }
     if (calls_back >= h->depth) return fail(h, B200RX_E_ARG, "b200rx_join: calls_back must be < pipeline depth");
     if (h->call_idx < (uint64_t)calls_back + 1) return B200RX_OK;
     CU(h, cudaSetDevice(h->device));
@@ -494,6 +531,17 @@ int b200rx_host_free(void *ptr)
     return cudaFreeHost(ptr) == cudaSuccess ? B200RX_OK : B200RX_E_CUDA;
 }
 
+int b200rx_host_is_pinned(const void *ptr)
+{
+    if (!ptr) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return at.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 int b200rx_device_counters(b200rx_handle *h, void **dev_ptr)
 {
     if (!h || !dev_ptr) return B200RX_E_ARG;
@@ -504,6 +552,8 @@ int b200rx_device_counters(b200rx_handle *h, void **dev_ptr)
 uint64_t b200rx_launch_count(const b200rx_handle *h) { return h ? h->launches : 0; }
 uint32_t b200rx_max_steps(const b200rx_handle *h) { return h ? h->max_steps : 0; }
 
+size_t b200rx_sample_bytes(const b200rx_handle *h) { return h ? sample_bytes(h->fmt) : 0; }
+
 namespace {
 
 struct OutPtrs { uint8_t *payload; uint32_t stride; uint16_t *len; uint8_t *rate; uint8_t *status; };
@@ -511,7 +561,8 @@ struct OutPtrs { uint8_t *payload; uint32_t stride; uint16_t *len; uint8_t *rate
 // K1 -> K2 -> K3 for frames [off, off + n) of the batch on stream s; ev (4 events) optional.
 int launch_range(b200rx_handle *h, const Tuning &tn, cudaStream_t s, uint32_t off, uint32_t n, const void *iq_dev, uint64_t iq_samples,
                  const uint64_t *lts1_dev, const uint32_t *avail_dev, const OutPtrs &o, const b200rx_debug *dbg,
-                 cudaEvent_t *ev, const FrameRot *rot_dev = nullptr, const uint32_t *n_live_dev = nullptr)
+                 cudaEvent_t *ev, const FrameRot *rot_dev = nullptr, const uint32_t *n_live_dev = nullptr,
+                 const uint8_t *select_dev = nullptr)
 {
     const size_t S = h->max_steps;
     FrontendArgs fa{};
@@ -530,6 +581,7 @@ int launch_range(b200rx_handle *h, const Tuning &tn, cudaStream_t s, uint32_t of
     fa.emit_pairs = tn.acs_gen == 3;
     fa.rot = rot_dev ? rot_dev + off : nullptr;
     fa.n_live = n_live_dev;
+    fa.select = select_dev ? select_dev + off : nullptr;
     if (dbg) {
         fa.dbg_eq = dbg->equalized ? reinterpret_cast<double2 *>(dbg->equalized) + (size_t)off * dbg->eq_vectors * 48 : nullptr;
         fa.dbg_eq_vectors = dbg->eq_vectors;
@@ -1029,6 +1081,231 @@ int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n_samples, double 
         if (lts1_out) CU(h, cudaMemcpyAsync(lts1_out, h->sy[li].lts1, nf * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     }
     CU(h, cudaStreamSynchronize(s));
+    return B200RX_OK;
+}
+
+// ---- two-phase passes (include/b200rx.h: b200rx_pass_*) ----
+namespace {
+
+// frame list of a scanned capture, written straight into host-mapped memory (one posted PCIe write per frame instead of
+// four device->host copies in front of the synchronisation the caller waits on)
+__global__ void pack_pass_kernel(const SyncSummary *summary, const uint64_t *lts1, const uint32_t *avail, const FrameDesc *desc,
+                                 uint32_t cap, SyncSummary *out_summary, b200rx_pass_frame *out)
+{
+    const uint32_t n = summary->n_frames < cap ? summary->n_frames : cap;
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f == 0) *out_summary = *summary;
+    if (f >= n) return;
+    const FrameDesc d = desc[f];
+    b200rx_pass_frame o;
+    o.lts1 = lts1[f];
+    o.avail = avail[f];
+    o.length = d.length;
+    o.rate = d.rate;
+    o.status = d.status;
+    out[f] = o;
+}
+
+int ensure_pass_lane(b200rx_handle *h, int li)
+{
+    b200rx_handle::PassLane &P = h->pl[li];
+    if (P.h_select) return B200RX_OK;
+    const size_t nf = h->limits.max_frames;
+    cudaError_t e = cudaSuccess;
+    if (!P.stream) e = cudaStreamCreateWithFlags(&P.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && !P.done) e = cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming);
+    uint8_t *d_status = nullptr, *d_select = nullptr, *h_list = nullptr, *h_select = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_status, nf);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_select, nf);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h_list, sizeof(SyncSummary) + nf * sizeof(b200rx_pass_frame), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h_select, nf, cudaHostAllocDefault);
+    void *dev = nullptr;
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dev, h_list, 0);
+    if (e != cudaSuccess) {
+        cudaFree(d_status); cudaFree(d_select);
+        if (h_list) cudaFreeHost(h_list);
+        if (h_select) cudaFreeHost(h_select);
+        (void)cudaGetLastError();
+        return fail(h, B200RX_E_NOMEM, "b200rx_pass_open: lane staging", e);
+    }
+    P.d_status = d_status; P.d_select = d_select; P.h_list = h_list; P.h_list_dev = (uint8_t *)dev; P.h_select = h_select;
+    return B200RX_OK;
+}
+
+} // namespace
+
+int b200rx_pass_open(b200rx_handle *h)
+{
+    if (!h) return B200RX_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    { int rcq = quiesce_host(h); if (rcq != B200RX_OK) return rcq; }
+    const int li = (int)(h->pass_count % h->depth);
+    if (h->lanes[li].stream && h->lanes[li].used) { // a device-buffer call still on this lane's scratch
+        CU(h, cudaStreamSynchronize(h->lanes[li].stream));
+        h->lanes[li].used = false;
+    }
+    if (li == 0) CU(h, cudaStreamSynchronize(h->stream)); // scratch set 0 also serves the synchronous entry points
+    int rc = ensure_pass_lane(h, li);
+    if (rc != B200RX_OK) return rc;
+    b200rx_handle::PassLane &P = h->pl[li];
+    if (P.busy) {
+        CU(h, cudaEventSynchronize(P.done));
+        P.busy = false;
+    }
+    P.fill = 0;
+    P.n_frames = 0;
+    P.scanned = false;
+    h->pass_lane = li;
+    h->pass_count++;
+    return B200RX_OK;
+}
+
+int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n_samples)
+{
+    if (!h) return B200RX_E_ARG;
+    if (h->pass_lane < 0) return fail(h, B200RX_E_ARG, "b200rx_pass_put: no pass open");
+    if (n_samples == 0) return B200RX_OK;
+    if (!iq) return fail(h, B200RX_E_ARG, "b200rx_pass_put: null argument");
+    b200rx_handle::PassLane &P = h->pl[h->pass_lane];
+    if (P.scanned) return fail(h, B200RX_E_ARG, "b200rx_pass_put: the pass has been scanned already");
+    CU(h, cudaSetDevice(h->device));
+    const size_t bps = sample_bytes(h->fmt);
+    const size_t need = (size_t)(P.fill + n_samples) * bps;
+    if (need > P.d_iq_cap) { // grow (the lane is idle apart from this pass's own copies)
+        size_t cap = P.d_iq_cap ? P.d_iq_cap : ((size_t)1 << 20);
+        while (cap < need) cap *= 2;
+        uint8_t *p = nullptr;
+        cudaError_t e = cudaMalloc((void **)&p, cap);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_pass_put: sample staging", e);
+        if (P.fill) CU(h, cudaMemcpyAsync(p, P.d_iq, (size_t)P.fill * bps, cudaMemcpyDeviceToDevice, P.stream));
+        CU(h, cudaStreamSynchronize(P.stream));
+        cudaFree(P.d_iq);
+        P.d_iq = p;
+        P.d_iq_cap = cap;
+    }
+    CU(h, cudaMemcpyAsync(P.d_iq + (size_t)P.fill * bps, iq, (size_t)n_samples * bps, cudaMemcpyHostToDevice, P.stream));
+    P.fill += n_samples;
+    return B200RX_OK;
+}
+
+int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frames, uint32_t frames_cap, b200rx_sync_result *res)
+{
+    if (!h) return B200RX_E_ARG;
+    if (!res || (!frames && frames_cap)) return fail(h, B200RX_E_ARG, "b200rx_pass_scan: null argument");
+    if (h->pass_lane < 0) return fail(h, B200RX_E_ARG, "b200rx_pass_scan: no pass open");
+    const int li = h->pass_lane;
+    b200rx_handle::PassLane &P = h->pl[li];
+    if (P.scanned) return fail(h, B200RX_E_ARG, "b200rx_pass_scan: the pass has been scanned already");
+    CU(h, cudaSetDevice(h->device));
+    memset(res, 0, sizeof(*res));
+    res->last_phase = phase_in;
+    P.scanned = true;
+    if (P.fill == 0) {
+        h->origins.clear();
+        return B200RX_OK;
+    }
+    cudaStream_t s = P.stream;
+    use_lane(h, li);
+    const uint32_t mf = h->limits.max_frames;
+    int rc = launch_sync_lane(h, s, li, P.d_iq, P.fill, phase_in, nullptr);
+    if (rc != B200RX_OK) return rc;
+    const b200rx_handle::SyncScratch &y = h->sy[li];
+    FrontendArgs fa{}; // SIGNAL decode of every frame found: descriptor with the full status logic
+    fa.iq = P.d_iq; fa.fmt = h->fmt; fa.scale = h->scale; fa.iq_samples = P.fill;
+    fa.lts1 = y.lts1; fa.avail = y.avail; fa.n_frames = mf; fa.desc = h->desc; fa.bm = h->bm;
+    fa.bm_stride = h->max_steps; fa.max_steps = h->max_steps; fa.max_len = h->limits.max_payload_bytes;
+    fa.header_only = 2; fa.hinv_out = h->hinv; fa.rot = y.rot; fa.n_live = &y.summary->n_frames;
+    CU(h, launch_frontend(fa, s));
+    SyncSummary *out_summary = reinterpret_cast<SyncSummary *>(P.h_list_dev);
+    b200rx_pass_frame *out_frames = reinterpret_cast<b200rx_pass_frame *>(P.h_list_dev + sizeof(SyncSummary));
+    pack_pass_kernel<<<(mf + 127) / 128, 128, 0, s>>>(y.summary, y.lts1, y.avail, h->desc, mf, out_summary, out_frames);
+    CU(h, cudaGetLastError());
+    h->launches += 2;
+    CU(h, cudaStreamSynchronize(s));
+    *res = *reinterpret_cast<const SyncSummary *>(P.h_list);
+    if (!res->phase_valid) res->last_phase = phase_in;
+    P.n_frames = res->n_frames < mf ? res->n_frames : mf;
+    const uint32_t n_copy = P.n_frames < frames_cap ? P.n_frames : frames_cap;
+    if (n_copy) memcpy(frames, P.h_list + sizeof(SyncSummary), (size_t)n_copy * sizeof(b200rx_pass_frame));
+    return B200RX_OK;
+}
+
+int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload_out, uint32_t payload_stride, uint8_t *status,
+                       uint64_t *ticket)
+{
+    if (!h) return B200RX_E_ARG;
+    if (!select || !status || !ticket) return fail(h, B200RX_E_ARG, "b200rx_pass_decode: null argument");
+    if (h->pass_lane < 0 || !h->pl[h->pass_lane].scanned) return fail(h, B200RX_E_ARG, "b200rx_pass_decode: no scanned pass");
+    const int li = h->pass_lane;
+    b200rx_handle::PassLane &P = h->pl[li];
+    if (P.busy) return fail(h, B200RX_E_ARG, "b200rx_pass_decode: the pass is being decoded already");
+    *ticket = 0;
+    const uint32_t n = P.n_frames;
+    uint32_t lo = n, hi = 0, n_sel = 0;
+    for (uint32_t f = 0; f < n; f++)
+        if (select[f]) {
+            if (f < lo) lo = f;
+            hi = f + 1;
+            n_sel++;
+        }
+    if (n_sel == 0) return B200RX_OK;
+    CU(h, cudaSetDevice(h->device));
+    cudaStream_t s = P.stream;
+    use_lane(h, li);
+    const size_t pl_bytes = payload_out ? (size_t)n * payload_stride : 0;
+    if (pl_bytes > P.d_payload_cap) {
+        cudaFree(P.d_payload); // idle: the lane's previous pass was waited for in b200rx_pass_open
+        P.d_payload = nullptr; P.d_payload_cap = 0;
+        cudaError_t e = cudaMalloc((void **)&P.d_payload, pl_bytes);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "b200rx_pass_decode: payload staging", e);
+        P.d_payload_cap = pl_bytes;
+    }
+    memcpy(P.h_select, select, n);
+    CU(h, cudaMemcpyAsync(P.d_select, P.h_select, n, cudaMemcpyHostToDevice, s));
+    CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
+    // A pass holds a handful of frames unless the caller hands over a long capture; what it owes the caller is a short
+    // tail behind the scan: the generation-2 ACS kernel with 16 lanes per frame takes 0.7 ms for 12 096 dependent steps
+    // however few frames there are, generation 3 is built for a full GPU
+    Tuning tn = h->tn;
+    if (tn.acs_gen == 3 && n_sel <= 2048) tn.acs_gen = 2;
+    const b200rx_handle::SyncScratch &y = h->sy[li];
+    const OutPtrs o{payload_out ? P.d_payload : nullptr, payload_stride, nullptr, nullptr, P.d_status};
+    int rc = launch_range(h, tn, s, lo, hi - lo, P.d_iq, P.fill, y.lts1, y.avail, o, nullptr, nullptr, y.rot, nullptr, P.d_select);
+    if (rc != B200RX_OK) return rc;
+    if (payload_out)
+        CU(h, cudaMemcpyAsync(payload_out + (size_t)lo * payload_stride, P.d_payload + (size_t)lo * payload_stride,
+                              (size_t)(hi - lo) * payload_stride, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(status + lo, P.d_status + lo, hi - lo, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaEventRecord(P.done, s));
+    P.busy = true;
+    P.ticket = h->pass_next_ticket++;
+    *ticket = P.ticket;
+    return B200RX_OK;
+}
+
+int b200rx_pass_poll(b200rx_handle *h, uint64_t ticket)
+{
+    if (!h) return B200RX_E_ARG;
+    if (ticket == 0) return 1;
+    for (auto &P : h->pl)
+        if (P.busy && P.ticket == ticket) {
+            cudaError_t e = cudaEventQuery(P.done);
+            if (e == cudaErrorNotReady) return 0;
+            if (e != cudaSuccess) return fail(h, B200RX_E_CUDA, "b200rx_pass_poll", e);
+            P.busy = false;
+            return 1;
+        }
+    return 1; // not in flight any more
+}
+
+int b200rx_pass_wait(b200rx_handle *h, uint64_t ticket)
+{
+    if (!h) return B200RX_E_ARG;
+    for (auto &P : h->pl)
+        if (P.busy && (ticket == 0 || P.ticket == ticket)) {
+            CU(h, cudaEventSynchronize(P.done));
+            P.busy = false;
+        }
     return B200RX_OK;
 }
 

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(
 
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (a.n_live && (uint32_t)frame >= *a.n_live) { // slot without a frame (raw-capture entry points)
+    if ((a.n_live && (uint32_t)frame >= *a.n_live) || (a.select && !a.select[frame])) { // slot without a frame (raw-capture
+                                                                                       // entry points) / frame not asked for
         if (tid == 0) {
             FrameDesc d;
             d.n_steps = 0; d.data_bits = 0; d.field = 0; d.length = 0;

@@ -139,6 +139,44 @@ def load_library():
     L.b200rx_launch_count.argtypes = [vp]
     L.b200rx_max_steps.restype = u32
     L.b200rx_max_steps.argtypes = [vp]
+    L.b200rx_sample_bytes.restype = C.c_size_t
+    L.b200rx_sample_bytes.argtypes = [vp]
+    L.b200rx_host_is_pinned.restype = C.c_int
+    L.b200rx_host_is_pinned.argtypes = [vp]
+    # two-phase passes (streaming callers)
+    L.b200rx_pass_open.restype = C.c_int
+    L.b200rx_pass_open.argtypes = [vp]
+    L.b200rx_pass_put.restype = C.c_int
+    L.b200rx_pass_put.argtypes = [vp, vp, u64]
+    L.b200rx_pass_scan.restype = C.c_int
+    L.b200rx_pass_scan.argtypes = [vp, C.c_double, vp, u32, C.POINTER(SyncResult)]
+    L.b200rx_pass_decode.restype = C.c_int
+    L.b200rx_pass_decode.argtypes = [vp, vp, vp, u32, vp, C.POINTER(u64)]
+    L.b200rx_pass_poll.restype = C.c_int
+    L.b200rx_pass_poll.argtypes = [vp, u64]
+    L.b200rx_pass_wait.restype = C.c_int
+    L.b200rx_pass_wait.argtypes = [vp, u64]
+    # several GPUs from one process
+    L.b200rx_group_create.restype = C.c_int
+    L.b200rx_group_create.argtypes = [vp, u32, C.POINTER(Limits), C.POINTER(vp)]
+    L.b200rx_group_destroy.restype = C.c_int
+    L.b200rx_group_destroy.argtypes = [vp]
+    L.b200rx_group_size.restype = u32
+    L.b200rx_group_size.argtypes = [vp]
+    L.b200rx_group_handle.restype = vp
+    L.b200rx_group_handle.argtypes = [vp, u32]
+    L.b200rx_group_last_error.restype = C.c_char_p
+    L.b200rx_group_last_error.argtypes = [vp]
+    L.b200rx_group_synchronize.restype = C.c_int
+    L.b200rx_group_synchronize.argtypes = [vp]
+    L.b200rx_group_plan.restype = C.c_int
+    L.b200rx_group_plan.argtypes = [vp, vp, u32, vp]
+    L.b200rx_group_decode_batch.restype = C.c_int
+    L.b200rx_group_decode_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, u32, vp, vp, vp]
+    L.b200rx_group_decode_batch_dev.restype = C.c_int
+    L.b200rx_group_decode_batch_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp]
+    L.b200rx_gather_status.restype = C.c_int
+    L.b200rx_gather_status.argtypes = [vp, vp, u32, vp, vp]
     _lib = L
     return L
 

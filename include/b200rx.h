@@ -154,6 +154,8 @@ B200RX_API int b200rx_join_on(b200rx_handle *h, uint32_t calls_back, void *cuda_
 /* Pinned host memory for the host-buffer entry point (plain malloc'ed memory also works, slower). */
 B200RX_API int b200rx_host_alloc(void **ptr, size_t bytes);
 B200RX_API int b200rx_host_free(void *ptr);
+/* 1 if ptr lies in pinned (page-locked) host memory known to CUDA, 0 if not. */
+B200RX_API int b200rx_host_is_pinned(const void *ptr);
 
 /* Replaces fft_symbols::work + channel_est::work + phase_tracker::work + frame_decoder::work
  * (fft_symbols.cpp:33-80, channel_est.cpp:36-85, phase_tracker.cpp:70-105, frame_decoder.cpp:45-91,
@@ -246,6 +248,47 @@ B200RX_API int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n_sampl
                               uint8_t *payload_out, uint32_t payload_stride, uint16_t *payload_len, uint8_t *rate_out,
                               uint8_t *status, uint64_t *lts1_out, b200rx_sync_result *res);
 
+/* ---- the same, as a two-phase pass for streaming callers (fun::b200_receiver_chain) ----
+ * receiver_chain::process_samples (receiver_chain.cpp:106-126) returns what its last block finished in EARLIER rounds: a
+ * frame surfaces up to five calls after the one that brought its samples (:118-125 swap the buffers one block down per
+ * call).  A pass uses that slack.  Phase one (open / put / scan) is short and synchronous - detection, synchronisation
+ * and SIGNAL decode of every frame in the capture, i.e. everything the caller's streaming state depends on (which
+ * frames exist, where, how long they are, m_phase_acc).  Phase two (decode) is the long dependent chain - data
+ * symbols, Viterbi, descrambler, CRC - and runs asynchronously: the caller collects it during a later call.  Up to
+ * `pipeline depth` passes (b200rx_set_pipeline_depth, 1..12) are in flight, each on its own lane (stream, scratch,
+ * sample staging), so single-frame Viterbi latency (12 096 dependent steps ~ 0.7 ms) overlaps with the following calls.
+ *
+ *   b200rx_pass_open    takes the next lane (waits for the pass that used it `depth` passes ago) and empties its staging
+ *   b200rx_pass_put     appends n_samples samples (handle's sample format) to the staging, asynchronously; pinned memory
+ *                       is copied by the DMA engine while the caller prepares the next slice; `iq` must stay untouched
+ *                       until b200rx_pass_scan returns
+ *   b200rx_pass_scan    frame_detector + timing_sync + ppdu::decode_header over the staged capture; returns when the
+ *                       frame list is on the host: frames[f] for f < res->n_frames (at most frames_cap are written).
+ *                       status: B200RX_ST_OK (header valid, all 128 + 80 * (1 + nsym) samples present), HDR_PARITY,
+ *                       HDR_RATE, TOO_LONG, or TRUNCATED (frame cut short by the next LTS1 or by the end of the capture)
+ *   b200rx_pass_decode  decodes the frames with select[f] != 0 (others are skipped); asynchronous.  Outputs are indexed
+ *                       by frame like b200rx_receive's and must stay valid until the pass is waited for; allocate them
+ *                       with b200rx_host_alloc.  A pass whose decode is never requested needs no wait.
+ *   b200rx_pass_poll    1 = that pass has finished (outputs are in place), 0 = still running
+ *   b200rx_pass_wait    blocks until it has
+ * b200rx_set_receive_origins applies to the next b200rx_pass_scan.  Passes and the other entry points of a handle must
+ * not be interleaved without b200rx_synchronize in between. */
+typedef struct b200rx_pass_frame {
+    uint64_t lts1;    /* capture index of the sample tagged LTS1 */
+    uint32_t avail;   /* samples from there to the next frame's LTS1 / the end of the capture */
+    uint16_t length;  /* LENGTH field (0 when the header failed) */
+    uint8_t rate;     /* fun::Rate or B200RX_RATE_INVALID */
+    uint8_t status;   /* header verdict, see above */
+} b200rx_pass_frame;
+B200RX_API int b200rx_pass_open(b200rx_handle *h);
+B200RX_API int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n_samples);
+B200RX_API int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frames, uint32_t frames_cap,
+                                b200rx_sync_result *res);
+B200RX_API int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload_out, uint32_t payload_stride,
+                                  uint8_t *status, uint64_t *ticket);
+B200RX_API int b200rx_pass_poll(b200rx_handle *h, uint64_t ticket);
+B200RX_API int b200rx_pass_wait(b200rx_handle *h, uint64_t ticket);
+
 /* Replaces ppdu::decode_header (ppdu.cpp:168-218) for n_frames frames: only the two LTS symbols and the
  * SIGNAL symbol are read (208 samples from lts1_index[f]); gives the streaming adapter the frame length
  * before the frame has fully arrived.  HOST buffers, synchronous.  status: B200RX_ST_OK (header valid; the
@@ -281,11 +324,59 @@ B200RX_API int b200rx_profile_read(b200rx_handle *h, uint32_t *calls, float *fro
  * reduce them with one collective (NCCL all-reduce) without a host round trip. */
 B200RX_API int b200rx_device_counters(b200rx_handle *h, void **dev_ptr);
 
+/* ---- several GPUs of one box from one process ----
+ * Frames are independent (all per-frame state is rebuilt from the frame's own LTS and SIGNAL symbols), so a batch is
+ * cut into contiguous shards, one per device, and there is no exchange on the data path.  A group owns one handle and
+ * one host thread per device; group calls fan out to the threads and return when every device has queued (device-buffer
+ * calls) or finished (host-buffer calls) its share.  The only collective is the gather of the per-frame status bytes
+ * and the sum of the counters after a decode (NCCL over NVLink: ncclCommInitAll, one communicator and one communication
+ * stream per device, ordered behind that device's decode by an event).  NCCL is loaded on first use (libnccl.so.2);
+ * everything except b200rx_gather_status works without it. */
+typedef struct b200rx_group b200rx_group;
+B200RX_API int b200rx_group_create(const int *devices, uint32_t n_devices, const b200rx_limits *limits_per_device,
+                                   b200rx_group **out);
+B200RX_API int b200rx_group_destroy(b200rx_group *g);
+B200RX_API uint32_t b200rx_group_size(const b200rx_group *g);
+B200RX_API b200rx_handle *b200rx_group_handle(b200rx_group *g, uint32_t i); /* for per-device settings (format, tuning, depth) */
+B200RX_API const char *b200rx_group_last_error(const b200rx_group *g);      /* g may be NULL: last group_create() error */
+B200RX_API int b200rx_group_synchronize(b200rx_group *g);
+
+/* Shard plan: first[i] .. first[i+1] is device i's range of frames (first has n_devices + 1 entries), contiguous and
+ * balanced by weight[f] (pass avail[]: a frame's samples are proportional to its trellis steps for a given rate; NULL =
+ * equal weights). */
+B200RX_API int b200rx_group_plan(const b200rx_group *g, const uint32_t *weight, uint32_t n_frames, uint32_t *first);
+
+/* b200rx_decode_batch over all devices of the group: same arguments, same outputs (frame f's results at index f); every
+ * device decodes its shard of the plan from the caller's host buffers with its own copy pipeline.  Returns when all
+ * outputs are in place.  n_frames may be up to n_devices * max_frames as long as no shard exceeds max_frames. */
+B200RX_API int b200rx_group_decode_batch(b200rx_group *g, const void *iq, uint64_t iq_samples, const uint64_t *lts1_index,
+                                         const uint32_t *avail, uint32_t n_frames, uint8_t *payload_out,
+                                         uint32_t payload_stride, uint16_t *payload_len, uint8_t *rate_out, uint8_t *status);
+
+/* b200rx_decode_batch_dev on every device at once: argument i of each array belongs to device i (pointers into that
+ * device's memory).  Asynchronous like the single-device call; b200rx_group_synchronize or b200rx_gather_status order
+ * the results. */
+B200RX_API int b200rx_group_decode_batch_dev(b200rx_group *g, const void *const *iq_dev, const uint64_t *iq_samples,
+                                             const uint64_t *const *lts1_index_dev, const uint32_t *const *avail_dev,
+                                             const uint32_t *n_frames, uint8_t *const *payload_out_dev, uint32_t payload_stride,
+                                             uint16_t *const *payload_len_dev, uint8_t *const *rate_out_dev,
+                                             uint8_t *const *status_dev);
+
+/* After a decode on every device: all-gather of frames_per_device status bytes from each device's status_dev[i] into
+ * gathered_dev[i] (n_devices * frames_per_device bytes on EVERY device, device-major; entries may be NULL to skip the
+ * gather) and all-reduce of the four counters of each device's most recent call {frames ok, frames failed, payload bytes
+ * of ok frames, trellis steps}, returned in counters_sum (host, 4 values; may be NULL).  Returns when both are complete. */
+B200RX_API int b200rx_gather_status(b200rx_group *g, const uint8_t *const *status_dev, uint32_t frames_per_device,
+                                    uint8_t *const *gathered_dev, uint64_t *counters_sum);
+
 /* Number of kernels launched by this handle since creation (for gpu_launches accounting). */
 B200RX_API uint64_t b200rx_launch_count(const b200rx_handle *h);
 
 /* Trellis capacity (steps per frame) the handle was sized for. */
 B200RX_API uint32_t b200rx_max_steps(const b200rx_handle *h);
+
+/* Bytes per complex sample in the handle's current sample format (16, 8 or 4). */
+B200RX_API size_t b200rx_sample_bytes(const b200rx_handle *h);
 
 #ifdef __cplusplus
 }

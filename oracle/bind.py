@@ -328,6 +328,21 @@ class Ref(_Lib):
         return [bytes(payload[i, : length[i]]) for i in range(n)]
 
 
+    def chain_run(self, chain, samples, chunk, drain=8, max_len=4095, max_frames=8192):
+        """The whole test_sim feed loop in native code (ref_harness.cpp: ref_chain_run).  Returns (payloads, seconds)."""
+        iq = _as_iq(samples)
+        payload = np.zeros((max_frames, max_len), dtype=np.uint8)
+        length = np.zeros(max_frames, dtype=np.int32)
+        sec = np.zeros(1, dtype=np.float64)
+        fn = self.lib.ref_chain_run
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        n = fn(chain, iq.ctypes.data, len(iq) // 2, int(chunk), int(drain), payload.ctypes.data, max_len, length.ctypes.data,
+               max_frames, sec.ctypes.data)
+        n = min(n, max_frames)
+        return [bytes(payload[i, : length[i]]) for i in range(n)], float(sec[0])
+
+
 class Port(_Lib):
     prefix = "orc"
     path = PORT_SO

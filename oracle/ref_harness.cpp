@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstring>
 #include <thread>
+#include <time.h>
 #include <vector>
 
 #include "block.h"
@@ -511,6 +512,35 @@ int ref_chain_process(void *chain, const double *iq, int n, uint8_t *payload_out
         }
         count++;
     }
+    return count;
+}
+
+/* The feed loop of examples/test_sim.cpp:77-97 in native code: chunks of `chunk` samples built as a std::vector and
+ * passed by value (test_sim.cpp:84-87), then `drain` zero chunks of 4096 samples (untimed) for the frames still inside the
+ * six-stage pipeline.  seconds = the feed loop only.  Returns the number of payloads; the first max_frames are copied. */
+int ref_chain_run(void *chain, const double *iq, long n, long chunk, int drain, uint8_t *payload_out, int payload_stride,
+                  int32_t *len_out, int max_frames, double *seconds)
+{
+    receiver_chain *rc = static_cast<receiver_chain *>(chain);
+    const cd *x = reinterpret_cast<const cd *>(iq);
+    int count = 0;
+    auto take = [&](const std::vector<std::vector<unsigned char> > &out) {
+        for (size_t k = 0; k < out.size(); k++, count++) {
+            if (count >= max_frames) continue;
+            int m = std::min((int)out[k].size(), payload_stride);
+            if (m) memcpy(payload_out + (size_t)count * payload_stride, out[k].data(), m);
+            len_out[count] = (int)out[k].size();
+        }
+    };
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (long s = 0; s < n; s += chunk) {
+        std::vector<cd> v(x + s, x + std::min(n, s + chunk));
+        take(rc->process_samples(v));
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int i = 0; i < drain; i++) take(rc->process_samples(std::vector<cd>(4096)));
+    *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     return count;
 }
 

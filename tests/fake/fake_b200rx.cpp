@@ -59,6 +59,11 @@ struct b200rx_handle {
     b200rx_limits lim;
     std::vector<int64_t> origins;
     std::string error;
+    // two-phase passes: the staged capture and what the reference made of it
+    std::vector<double> pass_iq;
+    std::vector<uint8_t> pass_payload, pass_status;
+    std::vector<uint16_t> pass_len;
+    uint32_t pass_frames = 0;
 };
 
 extern "C" {
@@ -139,5 +144,55 @@ int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n, double, uint8_t
     res->overflow = (uint32_t)(starts.size() - nf);
     return B200RX_OK;
 }
+
+
+// ---- two-phase passes: scan = the same capture logic, decode = hand out what the scan already computed ----
+int b200rx_set_pipeline_depth(b200rx_handle *, uint32_t) { return B200RX_OK; }
+int b200rx_host_is_pinned(const void *) { return 0; }
+int b200rx_pass_open(b200rx_handle *h) { h->pass_iq.clear(); h->pass_frames = 0; return B200RX_OK; }
+int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n)
+{
+    const double *p = (const double *)iq;
+    h->pass_iq.insert(h->pass_iq.end(), p, p + 2 * n);
+    return B200RX_OK;
+}
+int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frames, uint32_t cap, b200rx_sync_result *res)
+{
+    const uint32_t mf = h->lim.max_frames, stride = h->lim.max_payload_bytes ? h->lim.max_payload_bytes : 1;
+    h->pass_payload.assign((size_t)mf * stride, 0);
+    h->pass_status.assign(mf, B200RX_ST_NO_FRAME);
+    h->pass_len.assign(mf, 0);
+    std::vector<uint8_t> rate(mf);
+    std::vector<uint64_t> lts1(mf);
+    const uint64_t n = h->pass_iq.size() / 2;
+    int rc = b200rx_receive(h, h->pass_iq.data(), n, phase_in, h->pass_payload.data(), stride, h->pass_len.data(), rate.data(),
+                            h->pass_status.data(), lts1.data(), res);
+    if (rc != B200RX_OK) return rc;
+    h->pass_frames = res->n_frames;
+    for (uint32_t f = 0; f < res->n_frames && f < cap; f++) {
+        frames[f].lts1 = lts1[f];
+        frames[f].avail = (uint32_t)((f + 1 < res->n_frames ? lts1[f + 1] : n) - lts1[f]);
+        frames[f].length = h->pass_len[f];
+        frames[f].rate = rate[f];
+        const uint8_t st = h->pass_status[f];
+        frames[f].status = (st == B200RX_ST_CRC_FAIL) ? (uint8_t)B200RX_ST_OK : st; // the header verdict only
+    }
+    return B200RX_OK;
+}
+int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload, uint32_t stride, uint8_t *status, uint64_t *ticket)
+{
+    const uint32_t own = h->lim.max_payload_bytes ? h->lim.max_payload_bytes : 1;
+    *ticket = 0;
+    for (uint32_t f = 0; f < h->pass_frames; f++) {
+        if (!select[f]) continue;
+        *ticket = 1;
+        status[f] = h->pass_status[f];
+        if (payload && status[f] == B200RX_ST_OK)
+            memcpy(payload + (size_t)f * stride, h->pass_payload.data() + (size_t)f * own, h->pass_len[f] < stride ? h->pass_len[f] : stride);
+    }
+    return B200RX_OK;
+}
+int b200rx_pass_poll(b200rx_handle *, uint64_t) { return 1; }
+int b200rx_pass_wait(b200rx_handle *, uint64_t) { return B200RX_OK; }
 
 } // extern "C"

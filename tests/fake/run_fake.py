@@ -72,6 +72,20 @@ def main():
     ch.close()
     out["config1"] = {"reference": len(want), "adapter": len(got), "equal": got == want,
                       "all_equal_transmitted": all(g == payload for g in got)}
+    # fun::b200_receiver (callback + thread + pause / resume, receiver.cpp:42-77) on the same loopback stream
+    import ctypes as C
+    lib = C.CDLL(FAKE_HOST)
+    lib.b200host_receiver_run.restype = C.c_int
+    lib.b200host_receiver_run.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p]
+    iq = np.ascontiguousarray(x).view(np.float64)
+    pl = np.zeros((256, 1500), np.uint8)
+    ln = np.zeros(256, np.int32)
+    paused = C.c_long(-5)
+    n = lib.b200host_receiver_run(iq.ctypes.data, len(x), 4096, 6, 30, 256, 1500, pl.ctypes.data, 1500, ln.ctypes.data, 256,
+                                  C.byref(paused))
+    rx_got = [bytes(pl[i, : ln[i]]) for i in range(max(n, 0))]
+    out["receiver"] = {"payloads": n, "equal": rx_got == want, "rounds_while_paused": int(paused.value)}
     # the block adapter on random streams tagged by the reference's own frame_detector + timing_sync
     out["block_random"] = []
     for s in range(n_streams):

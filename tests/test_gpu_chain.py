@@ -15,16 +15,47 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class Chain:
-    def __init__(self, max_frames=256, max_payload=4095, lib_path=None):
+    def __init__(self, max_frames=256, max_payload=4095, lib_path=None, depth=None, max_lag=5):
         self.lib = C.CDLL(lib_path or os.path.join(ROOT, "fun_ofdm_b200", "lib", "libb200host.so"))
         self.lib.b200host_chain_new.restype = C.c_void_p
         self.lib.b200host_chain_new.argtypes = [C.c_int, C.c_uint, C.c_uint]
+        self.lib.b200host_chain_new2.restype = C.c_void_p
+        self.lib.b200host_chain_new2.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+        self.lib.b200host_chain_run.restype = C.c_int
+        self.lib.b200host_chain_run.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_int, C.c_void_p]
+        self.lib.b200host_alloc_samples.restype = C.c_void_p
+        self.lib.b200host_alloc_samples.argtypes = [C.c_long]
+        self.lib.b200host_free_samples.argtypes = [C.c_void_p]
         self.lib.b200host_chain_process.restype = C.c_int
         self.lib.b200host_chain_process.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         self.lib.b200host_chain_delete.argtypes = [C.c_void_p]
         self.lib.b200host_chain_counters.argtypes = [C.c_void_p, C.c_void_p]
-        self.h = self.lib.b200host_chain_new(0, max_frames, max_payload)
+        if depth is None:
+            self.h = self.lib.b200host_chain_new(0, max_frames, max_payload)
+        else:
+            self.h = self.lib.b200host_chain_new2(0, max_frames, max_payload, depth, max_lag)
         assert self.h, "b200_receiver_chain could not be created (no GPU?)"
+
+    def run(self, samples, chunk, by_value=False, max_out=4096, stride=4095, pinned=False):
+        """The whole feed loop + flush in native code (host_capi.cpp: b200host_chain_run).  Returns (payloads, seconds of
+        the feed loop, seconds including the flush).  pinned: the stream is first copied into pinned memory (not timed)."""
+        payload = np.zeros((max_out, stride), np.uint8)
+        length = np.zeros(max_out, np.int32)
+        sec = np.zeros(2, np.float64)
+        iq = np.ascontiguousarray(samples, dtype=np.complex128).view(np.float64)
+        ptr, pin = iq.ctypes.data, None
+        if pinned:
+            pin = self.lib.b200host_alloc_samples(len(iq) // 2)
+            assert pin
+            C.memmove(pin, iq.ctypes.data, iq.nbytes)
+            ptr = pin
+        n = self.lib.b200host_chain_run(self.h, ptr, len(iq) // 2, chunk, 1 if by_value else 0, payload.ctypes.data, stride,
+                                        length.ctypes.data, max_out, sec.ctypes.data)
+        if pin:
+            self.lib.b200host_free_samples(pin)
+        assert n <= max_out
+        return [bytes(payload[i, : length[i]]) for i in range(n)], float(sec[0]), float(sec[1])
 
     def process(self, samples, max_out=512, stride=4095):
         """samples=None: flush"""
@@ -144,3 +175,75 @@ def test_randomised_streams_match_reference_chain(ref):
         total += len(want2)
     rx.close()
     assert total > 40
+
+
+@pytest.mark.parametrize("depth,lag", [(1, 0), (2, 1), (6, 5), (12, 11)])
+def test_pipelined_passes_deliver_the_same_sequence(ref, depth, lag):
+    """The two-phase passes (b200rx_pass_*): whatever the number of passes in flight and the delivery lag, the payload
+    SEQUENCE equals the reference chain's; only the call a frame surfaces in moves (the reference itself delivers up to
+    five calls late, receiver_chain.cpp:118-125)."""
+    rng = np.random.default_rng(77 + depth)
+    rates = [int(r) for r in rng.integers(0, 11, 24)]
+    lengths = [int(v) for v in rng.integers(0, 900, 24)]
+    x, _ = _capture(ref, rng, rates, lengths, 22, gap=450, lead=300, tail=4096)
+    for chunk in (4096, 1500):
+        want = _reference_chain(ref, x, chunk)
+        ch = Chain(depth=depth, max_lag=lag)
+        got, lagged = [], 0
+        for s in range(0, len(x), chunk):
+            out = ch.process(x[s: s + chunk])
+            got += out
+        tail = ch.process(None)
+        lagged = len(tail)
+        got += tail
+        c = ch.counters()
+        ch.close()
+        assert got == want, (depth, lag, chunk, len(got), len(want), c)
+        assert len(got) >= 12, c
+        if lag == 0:
+            assert lagged <= 1  # synchronous: nothing but a frame completed by the flush pad is left for the flush
+
+
+def test_native_feed_loop_by_value_pointer_and_pinned(ref):
+    """b200host_chain_run = the loop of examples/test_sim.cpp:77-97 in native code: by-value std::vector like test_sim,
+    the pointer overload, and a pinned caller buffer with calls long enough (>= 65 536 samples) to be copied to the GPU
+    straight from it - all against the reference chain fed the same chunks."""
+    rng = np.random.default_rng(2027)
+    rates = [int(r) for r in rng.integers(0, 11, 60)]
+    lengths = [int(v) for v in rng.integers(0, 1200, 60)]
+    x, _ = _capture(ref, rng, rates, lengths, 24, gap=420, lead=300, tail=8192)
+    for chunk, by_value, pinned in ((4096, True, False), (4096, False, False), (70000, False, True), (70000, True, False),
+                                    (200000, False, True)):
+        want = _reference_chain(ref, x, chunk)
+        ch = Chain(max_frames=512)
+        got, t_feed, t_all = ch.run(x, chunk, by_value=by_value, pinned=pinned)
+        c = ch.counters()
+        ch.close()
+        assert got == want, (chunk, by_value, pinned, len(got), len(want), c)
+        assert len(got) >= 40 and t_all >= t_feed > 0.0
+
+
+def test_receiver_wrapper_callback_pause_resume(ref):
+    """fun::b200_receiver = the reference's fun::receiver loop (receiver.cpp:42-58: get_samples -> process_samples ->
+    callback, pause / resume around it) over a sample-source functor: same payload sequence as the reference chain fed
+    the same 4096-sample rounds, and no round runs while the receiver is paused."""
+    rng = np.random.default_rng(515)
+    rates = [int(r) for r in rng.integers(0, 11, 30)]
+    lengths = [int(v) for v in rng.integers(0, 800, 30)]
+    x, _ = _capture(ref, rng, rates, lengths, 25, gap=450, lead=300, tail=6 * 4096)
+    x = x[: (len(x) // 4096) * 4096]
+    want = _reference_chain(ref, x, 4096)
+    lib = C.CDLL(os.path.join(ROOT, "fun_ofdm_b200", "lib", "libb200host.so"))
+    lib.b200host_receiver_run.restype = C.c_int
+    lib.b200host_receiver_run.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p]
+    iq = np.ascontiguousarray(x).view(np.float64)
+    pl = np.zeros((256, 4095), np.uint8)
+    ln = np.zeros(256, np.int32)
+    paused = C.c_long(-5)
+    n = lib.b200host_receiver_run(iq.ctypes.data, len(x), 4096, 5, 40, 256, 4095, pl.ctypes.data, 4095, ln.ctypes.data, 256,
+                                  C.byref(paused))
+    assert n >= 20
+    got = [bytes(pl[i, : ln[i]]) for i in range(n)]
+    assert got == want, (len(got), len(want))
+    assert paused.value == 0

@@ -41,6 +41,8 @@ def test_adapters_match_reference_on_chunked_streams(fake_built, seed):
     for b in out["block"]:
         assert b["equal"] and b["adapter"] >= 11, b
     assert out["config1"]["equal"] and out["config1"]["adapter"] == 40 and out["config1"]["all_equal_transmitted"], out["config1"]
+    # fun::b200_receiver: same payload sequence through the callback; no round runs while the receiver is paused
+    assert out["receiver"]["equal"] and out["receiver"]["payloads"] == 40 and out["receiver"]["rounds_while_paused"] == 0, out["receiver"]
     assert len(out["block_random"]) == 12
     for b in out["block_random"]:
         assert b["equal"], b

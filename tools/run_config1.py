@@ -34,32 +34,44 @@ def main():
     data = b"I'm a little tea pot, short and stout.....here is my handle.....blah blah blah.....this rhyme sucks!"
     payload = data * 15
     frame = ref.build_frame(payload, 8)
+    bits = 8 * len(payload)
     points = []
-    for n_frames, chunk in ((100, 4096), (2000, 4096), (2000, 65536), (2000, 1 << 20)):
+    warm = Chain(max_frames=2048, max_payload=1500)  # CUDA context, module load
+    warm.run(np.tile(frame, 4), 4096)
+    warm.close()
+    for n_frames, chunk in ((100, 4096), (2000, 4096), (8000, 65536), (8000, 1 << 20)):
         x = np.concatenate([np.tile(frame, n_frames), np.zeros(10 * len(frame), complex)])
         chain = ref.chain_new()
-        want, t_ref = feed(lambda c: ref.chain_process(chain, c, max_frames=2048), x, chunk)
-        for _ in range(8):  # drain the reference pipeline (not timed; one round per block)
-            want += ref.chain_process(chain, np.zeros(4096, complex), max_frames=2048)
-        g = Chain(max_frames=2048, max_payload=1500)
-        g.process(x[: 4 * len(frame)], max_out=2048, stride=1500)  # warm-up: CUDA context, staging buffers
-        g.close()
-        g = Chain(max_frames=2048, max_payload=1500)
-        g.process(np.zeros(64, complex))
-        got, t_gpu = feed(lambda c: g.process(c, max_out=2048, stride=1500), x, chunk)
-        got += g.process(None)
-        g.close()
-        bits = 8 * len(payload)
-        points.append({"frames": n_frames, "chunk_samples": chunk, "samples": int(len(x)),
-                       "reference_chain": {"payloads": len(want), "seconds": t_ref, "mbit_s": len(want) * bits / t_ref / 1e6,
-                                           "msamples_s": len(x) / t_ref / 1e6},
-                       "b200_receiver_chain": {"payloads": len(got), "seconds": t_gpu, "mbit_s": len(got) * bits / t_gpu / 1e6,
-                                               "msamples_s": len(x) / t_gpu / 1e6},
-                       "payload_sequences_identical": got == want, "all_payloads_equal_transmitted": all(p == payload for p in got)})
+        want, t_ref = ref.chain_run(chain, x, chunk, drain=8, max_len=1500)  # native loop; the drain is not timed
+        point = {"frames": n_frames, "chunk_samples": chunk, "samples": int(len(x)),
+                 "reference_chain": {"payloads": len(want), "seconds": t_ref, "mbit_s": len(want) * bits / t_ref / 1e6,
+                                     "msamples_s": len(x) / t_ref / 1e6}, "b200_receiver_chain": {}}
+        # variants of the same feed loop (native, host_capi.cpp b200host_chain_run; seconds include the final flush):
+        #   test_sim      std::vector built per chunk and passed by value, exactly as examples/test_sim.cpp:84-87
+        #   pointer       process_samples(const complex<double>*, n) on pageable memory
+        #   pinned        the caller's samples already lie in pinned memory (alloc_samples), e.g. a radio driver's buffer
+        #   lag           depth / max_lag: passes in flight / calls a payload may stay behind (5 = the reference's own)
+        variants = [("test_sim_by_value_depth6_lag5", dict(by_value=True), dict(depth=6, max_lag=5)),
+                    ("pointer_depth6_lag5", dict(), dict(depth=6, max_lag=5)),
+                    ("pointer_depth12_lag11", dict(), dict(depth=12, max_lag=11)),
+                    ("pointer_depth1_synchronous", dict(), dict(depth=1, max_lag=0)),
+                    ("pinned_depth6_lag5", dict(pinned=True), dict(depth=6, max_lag=5))]
+        for name, run_kw, new_kw in variants:
+            g = Chain(max_frames=2048, max_payload=1500, **new_kw)
+            # untimed: every lane allocates its staging on first use (cudaMalloc / cudaHostAlloc take milliseconds)
+            g.run(x[: min(len(x), 14 * chunk)], chunk, max_out=8192, stride=1500, **run_kw)
+            got, t_feed, t_all = g.run(x, chunk, max_out=8192, stride=1500, **run_kw)
+            g.close()
+            point["b200_receiver_chain"][name] = {
+                "payloads": len(got), "seconds": t_all, "seconds_feed_loop": t_feed, "mbit_s": len(got) * bits / t_all / 1e6,
+                "msamples_s": len(x) / t_all / 1e6, "us_per_call": 1e6 * t_feed / max(1, -(-len(x) // chunk)),
+                "payload_sequence_identical_to_reference": got == want,
+                "all_payloads_equal_transmitted": all(p == payload for p in got)}
+        points.append(point)
     print(json.dumps({"config": "1: test_sim loopback, RATE_3_4_QAM16, 1500-byte ASCII payload, frames back to back, noiseless; "
                                 "reference = its six-thread receiver_chain on %d host cores (FFTW/Boost replaced by "
-                                "oracle/shims), GPU = fun::b200_receiver_chain on one B200, host std::vector in, payloads out"
-                                % (os.cpu_count() or 1), "points": points}), flush=True)
+                                "oracle/shims), fed from Python per chunk; GPU = fun::b200_receiver_chain on one B200, host "
+                                "samples in, payloads out, native feed loop" % (os.cpu_count() or 1), "points": points}), flush=True)
     os._exit(0)  # the reference chain's threads never join
 
 
