@@ -104,7 +104,7 @@ struct b200rx_handle {
         uint8_t *h_select = nullptr;                           // pinned [max_frames]
         uint64_t fill = 0;                                     // samples staged so far
         uint32_t n_frames = 0;
-        bool scanned = false, busy = false;
+        bool scanned = false, busy = false, tagged = false;
         uint64_t ticket = 0;
     };
     PassLane pl[B200RX_MAX_PIPELINE_DEPTH];
@@ -404,7 +404,7 @@ int b200rx_set_stream(b200rx_handle *h, void *cuda_stream)
 int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale)
 {
     if (!h) return B200RX_E_ARG;
-    if (format != B200RX_FMT_FC64 && format != B200RX_FMT_FC32 && format != B200RX_FMT_SC16)
+    if (format != B200RX_FMT_FC64 && format != B200RX_FMT_FC32 && format != B200RX_FMT_SC16 && format != B200RX_FMT_TAGGED_FC64)
         return fail(h, B200RX_E_ARG, "b200rx_set_sample_format: unknown format");
     if (format == B200RX_FMT_SC16 && !(sc16_scale > 0.0)) return fail(h, B200RX_E_ARG, "b200rx_set_sample_format: scale must be > 0");
     h->fmt = format;
@@ -794,7 +794,7 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     // Pinned caller buffer: the GPU can pull the useful samples itself (ingest.cu) instead of a DMA copy of everything.
     // pull_mode 0: always DMA-copy, 1: pull whenever the buffer is pinned, 2: alternate, -1: by format (narrow formats:
     // the DMA engine wins)
-    const int pull_mode = h->tn.pull_mode >= 0 ? h->tn.pull_mode : (h->fmt == FMT_FC64 ? 1 : 0);
+    const int pull_mode = h->fmt == FMT_TAGGED ? 0 : (h->tn.pull_mode >= 0 ? h->tn.pull_mode : (h->fmt == FMT_FC64 ? 1 : 0));
     const bool pull_wanted = pull_mode != 0;
     const void *iq_mapped = nullptr;
     if (pull_wanted) {
@@ -893,7 +893,9 @@ int ensure_sync_scratch(b200rx_handle *h, int lane)
     b200rx_handle::SyncScratch &y = h->sy[lane];
     if (e == cudaSuccess && !y.summary) {
         auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-        A((void **)&y.ev_x, h->sy_ev_cap * sizeof(uint64_t));
+        size_t ev_pow2 = 64; // the tagged scan sorts the list in place (bitonic): room for the next power of two
+        while (ev_pow2 < h->sy_ev_cap) ev_pow2 *= 2;
+        A((void **)&y.ev_x, ev_pow2 * sizeof(uint64_t));
         A((void **)&y.ev_count, 2 * sizeof(uint32_t));
         A((void **)&y.rec, h->sy_ev_cap * sizeof(SyncRec));
         A((void **)&y.lts1, nf * sizeof(uint64_t));
@@ -910,6 +912,7 @@ int ensure_sync_scratch(b200rx_handle *h, int lane)
 int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const void *iq_dev, uint64_t n_samples, double phase_in,
                      uint8_t *tags_dev)
 {
+    if (h->fmt == FMT_TAGGED) return fail(h, B200RX_E_ARG, "tagged samples have been synchronised already: not a raw capture");
     int rc = ensure_sync_scratch(h, lane);
     if (rc != B200RX_OK) return rc;
     b200rx_handle::SyncScratch &y = h->sy[lane];
@@ -1106,6 +1109,57 @@ __global__ void pack_pass_kernel(const SyncSummary *summary, const uint64_t *lts
     out[f] = o;
 }
 
+// ---- tagged streams (b200rx_pass_scan_tagged): find the LTS1 tags, list the frames ----
+// Every sample's tag is looked at once; the few positions found are appended in any order ...
+__global__ void tag_find_kernel(const char *stream, uint64_t n_samples, uint64_t *pos, uint32_t *count, uint32_t cap)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples) return;
+    const int tag = *reinterpret_cast<const int *>(stream + i * TAGGED_SAMPLE_BYTES + 16);
+    if (tag != TAG_LTS1) return;
+    const uint32_t k = atomicAdd(count, 1u);
+    if (k < cap) pos[k] = i;
+}
+
+// ... and one CTA puts them in stream order (bitonic sort, in place) and writes the frame list: a frame reaches to the
+// next LTS1 or to the end of the stream (fft_symbols.cpp:42-51).
+__global__ void __launch_bounds__(1024) tag_frames_kernel(uint64_t *pos, const uint32_t *count, uint32_t cap, uint32_t max_frames,
+                                                          uint64_t n_samples, uint64_t *lts1, uint32_t *avail, SyncSummary *summary)
+{
+    const uint32_t found = *count;
+    const uint32_t n = found < cap ? found : cap;
+    uint32_t n2 = 1;
+    while (n2 < n) n2 *= 2;
+    for (uint32_t i = n + threadIdx.x; i < n2; i += blockDim.x) pos[i] = ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k *= 2)
+        for (uint32_t j = k / 2; j > 0; j /= 2) {
+            for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const uint64_t a = pos[i], b = pos[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { pos[i] = b; pos[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const uint32_t nf = n < max_frames ? n : max_frames;
+    for (uint32_t f = threadIdx.x; f < nf; f += blockDim.x) {
+        const uint64_t a = pos[f];
+        const uint64_t e = (f + 1 < n) ? pos[f + 1] : n_samples;
+        lts1[f] = a;
+        avail[f] = (uint32_t)(e - a < 0xFFFFFFFFull ? e - a : 0xFFFFFFFFull);
+    }
+    if (threadIdx.x == 0) {
+        SyncSummary s{};
+        s.n_events = found;
+        s.n_frames = nf;
+        s.overflow = found - nf;
+        *summary = s;
+    }
+}
+
 int ensure_pass_lane(b200rx_handle *h, int li)
 {
     b200rx_handle::PassLane &P = h->pl[li];
@@ -1155,6 +1209,7 @@ int b200rx_pass_open(b200rx_handle *h)
     P.fill = 0;
     P.n_frames = 0;
     P.scanned = false;
+    P.tagged = false;
     h->pass_lane = li;
     h->pass_count++;
     return B200RX_OK;
@@ -1188,10 +1243,14 @@ int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n_samples)
     return B200RX_OK;
 }
 
-int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frames, uint32_t frames_cap, b200rx_sync_result *res)
+static int pass_scan_impl(b200rx_handle *h, bool tagged, double phase_in, b200rx_pass_frame *frames, uint32_t frames_cap,
+                          b200rx_sync_result *res)
 {
     if (!h) return B200RX_E_ARG;
     if (!res || (!frames && frames_cap)) return fail(h, B200RX_E_ARG, "b200rx_pass_scan: null argument");
+    if (tagged != (h->fmt == FMT_TAGGED))
+        return fail(h, B200RX_E_ARG, tagged ? "b200rx_pass_scan_tagged: the sample format must be B200RX_FMT_TAGGED_FC64"
+                                            : "b200rx_pass_scan: tagged samples have been synchronised already (b200rx_pass_scan_tagged)");
     if (h->pass_lane < 0) return fail(h, B200RX_E_ARG, "b200rx_pass_scan: no pass open");
     const int li = h->pass_lane;
     b200rx_handle::PassLane &P = h->pl[li];
@@ -1200,6 +1259,7 @@ int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frame
     memset(res, 0, sizeof(*res));
     res->last_phase = phase_in;
     P.scanned = true;
+    P.tagged = tagged;
     if (P.fill == 0) {
         h->origins.clear();
         return B200RX_OK;
@@ -1207,14 +1267,27 @@ int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frame
     cudaStream_t s = P.stream;
     use_lane(h, li);
     const uint32_t mf = h->limits.max_frames;
-    int rc = launch_sync_lane(h, s, li, P.d_iq, P.fill, phase_in, nullptr);
-    if (rc != B200RX_OK) return rc;
+    int rc;
+    if (tagged) {
+        rc = ensure_sync_scratch(h, li);
+        if (rc != B200RX_OK) return rc;
+        const b200rx_handle::SyncScratch &t = h->sy[li];
+        CU(h, cudaMemsetAsync(t.ev_count, 0, 2 * sizeof(uint32_t), s));
+        tag_find_kernel<<<(unsigned)((P.fill + 255) / 256), 256, 0, s>>>(reinterpret_cast<const char *>(P.d_iq), P.fill, t.ev_x,
+                                                                        t.ev_count, h->sy_ev_cap);
+        tag_frames_kernel<<<1, 1024, 0, s>>>(t.ev_x, t.ev_count, h->sy_ev_cap, mf, P.fill, t.lts1, t.avail, t.summary);
+        CU(h, cudaGetLastError());
+        h->launches += 2;
+    } else {
+        rc = launch_sync_lane(h, s, li, P.d_iq, P.fill, phase_in, nullptr);
+        if (rc != B200RX_OK) return rc;
+    }
     const b200rx_handle::SyncScratch &y = h->sy[li];
     FrontendArgs fa{}; // SIGNAL decode of every frame found: descriptor with the full status logic
     fa.iq = P.d_iq; fa.fmt = h->fmt; fa.scale = h->scale; fa.iq_samples = P.fill;
     fa.lts1 = y.lts1; fa.avail = y.avail; fa.n_frames = mf; fa.desc = h->desc; fa.bm = h->bm;
     fa.bm_stride = h->max_steps; fa.max_steps = h->max_steps; fa.max_len = h->limits.max_payload_bytes;
-    fa.header_only = 2; fa.hinv_out = h->hinv; fa.rot = y.rot; fa.n_live = &y.summary->n_frames;
+    fa.header_only = 2; fa.hinv_out = h->hinv; fa.rot = tagged ? nullptr : y.rot; fa.n_live = &y.summary->n_frames;
     CU(h, launch_frontend(fa, s));
     SyncSummary *out_summary = reinterpret_cast<SyncSummary *>(P.h_list_dev);
     b200rx_pass_frame *out_frames = reinterpret_cast<b200rx_pass_frame *>(P.h_list_dev + sizeof(SyncSummary));
@@ -1228,6 +1301,16 @@ int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frame
     const uint32_t n_copy = P.n_frames < frames_cap ? P.n_frames : frames_cap;
     if (n_copy) memcpy(frames, P.h_list + sizeof(SyncSummary), (size_t)n_copy * sizeof(b200rx_pass_frame));
     return B200RX_OK;
+}
+
+int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frames, uint32_t frames_cap, b200rx_sync_result *res)
+{
+    return pass_scan_impl(h, false, phase_in, frames, frames_cap, res);
+}
+
+int b200rx_pass_scan_tagged(b200rx_handle *h, b200rx_pass_frame *frames, uint32_t frames_cap, b200rx_sync_result *res)
+{
+    return pass_scan_impl(h, true, 0.0, frames, frames_cap, res);
 }
 
 int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload_out, uint32_t payload_stride, uint8_t *status,
@@ -1270,7 +1353,8 @@ int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload
     if (tn.acs_gen == 3 && n_sel <= 2048) tn.acs_gen = 2;
     const b200rx_handle::SyncScratch &y = h->sy[li];
     const OutPtrs o{payload_out ? P.d_payload : nullptr, payload_stride, nullptr, nullptr, P.d_status};
-    int rc = launch_range(h, tn, s, lo, hi - lo, P.d_iq, P.fill, y.lts1, y.avail, o, nullptr, nullptr, y.rot, nullptr, P.d_select);
+    int rc = launch_range(h, tn, s, lo, hi - lo, P.d_iq, P.fill, y.lts1, y.avail, o, nullptr, nullptr, P.tagged ? nullptr : y.rot,
+                          nullptr, P.d_select);
     if (rc != B200RX_OK) return rc;
     if (payload_out)
         CU(h, cudaMemcpyAsync(payload_out + (size_t)lo * payload_stride, P.d_payload + (size_t)lo * payload_stride,

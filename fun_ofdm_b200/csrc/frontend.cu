@@ -644,6 +644,7 @@ cudaError_t launch_frontend_data(const FrontendArgs &a, cudaStream_t s)
         case FMT_FC32 * 2 + 1: DK_LAUNCH(true, FMT_FC32); break;
         case FMT_SC16 * 2: DK_LAUNCH(false, FMT_SC16); break;
         case FMT_SC16 * 2 + 1: DK_LAUNCH(true, FMT_SC16); break;
+        case FMT_TAGGED * 2: DK_LAUNCH(false, FMT_TAGGED); break; // a tagged stream has been rotated by timing_sync already
         default: return cudaErrorInvalidValue;
     }
 #undef DK_LAUNCH
@@ -664,6 +665,7 @@ cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s)
         case FMT_FC32 * 2 + 1: FE_LAUNCH(true, FMT_FC32); break;
         case FMT_SC16 * 2: FE_LAUNCH(false, FMT_SC16); break;
         case FMT_SC16 * 2 + 1: FE_LAUNCH(true, FMT_SC16); break;
+        case FMT_TAGGED * 2: FE_LAUNCH(false, FMT_TAGGED); break;
         default: return cudaErrorInvalidValue;
     }
 #undef FE_LAUNCH

@@ -113,9 +113,17 @@ __host__ __device__ __forceinline__ uint32_t branch_class(uint32_t j)
 // are the narrower formats the same samples have before UHD widens them on the host.  The widening to
 // double happens in the load, exactly (float -> double) or with one rounding ((double)int16 * scale), so the kernels
 // compute what the reference computes when it is handed the widened samples.
-enum { FMT_FC64 = B200RX_FMT_FC64, FMT_FC32 = B200RX_FMT_FC32, FMT_SC16 = B200RX_FMT_SC16 };
+enum { FMT_FC64 = B200RX_FMT_FC64, FMT_FC32 = B200RX_FMT_FC32, FMT_SC16 = B200RX_FMT_SC16, FMT_TAGGED = B200RX_FMT_TAGGED_FC64 };
 
-__host__ __device__ __forceinline__ size_t sample_bytes(int fmt) { return fmt == FMT_FC64 ? 16 : (fmt == FMT_FC32 ? 8 : 4); }
+// FMT_TAGGED: the reference's own element type between timing_sync and fft_symbols, fun::tagged_sample
+// (tagged_vector.h:82-94): { std::complex<double> sample; vector_tag tag; } = 16 + 4 + 4 padding bytes.
+constexpr size_t TAGGED_SAMPLE_BYTES = 24;
+constexpr int TAG_LTS1 = 4; // tagged_vector.h:25-34
+
+__host__ __device__ __forceinline__ size_t sample_bytes(int fmt)
+{
+    return fmt == FMT_FC64 ? 16 : (fmt == FMT_FC32 ? 8 : (fmt == FMT_SC16 ? 4 : TAGGED_SAMPLE_BYTES));
+}
 
 #ifdef __CUDACC__
 template <int FMT>
@@ -126,6 +134,9 @@ __device__ __forceinline__ double2 load_sample(const void *base, uint64_t i, dou
     } else if constexpr (FMT == FMT_FC32) {
         const float2 v = reinterpret_cast<const float2 *>(base)[i];
         return make_double2((double)v.x, (double)v.y);
+    } else if constexpr (FMT == FMT_TAGGED) { // 24-byte structs: 8-byte aligned, two loads
+        const double *q = reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + i * TAGGED_SAMPLE_BYTES);
+        return make_double2(q[0], q[1]);
     } else {
         const short2 v = reinterpret_cast<const short2 *>(base)[i];
         return make_double2(__dmul_rn((double)v.x, scale), __dmul_rn((double)v.y, scale));

@@ -40,7 +40,10 @@ namespace fun
             if (!more) break;
             std::this_thread::yield(); // gives a pause() caller waiting for the round to end its turn
         }
-        m_callback(m_chain.flush());                                 // the payloads still in flight
+        {
+            std::lock_guard<std::mutex> round(m_pause);              // a paused receiver hands nothing to the callback
+            m_callback(m_chain.flush());                             // the payloads still in flight
+        }
         {
             std::lock_guard<std::mutex> l(m_done_mu);
             m_done = true;

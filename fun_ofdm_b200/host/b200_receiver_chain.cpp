@@ -114,7 +114,7 @@ namespace fun
         m_depth(depth < 1 ? 1 : (depth > B200RX_MAX_PIPELINE_DEPTH ? B200RX_MAX_PIPELINE_DEPTH : depth)),
         m_max_lag(max_lag),
         m_buf(nullptr), m_buf_n(0), m_buf_cap(0),
-        m_base(0), m_handled(0), m_last_lts1(-1), m_pending_lts1(-1), m_phase(0.0),
+        m_base(0), m_handled(0), m_stream_start(0), m_last_lts1(-1), m_pending_lts1(-1), m_phase(0.0),
         m_pass_seq(0), m_frames(nullptr), m_pool(nullptr)
     {
         std::memset(&m_counters, 0, sizeof(m_counters));
@@ -265,10 +265,14 @@ namespace fun
     {
         std::vector<std::vector<unsigned char> > out = process_samples(std::vector<std::complex<double> >(pad));
         collect(out, true);
+        // whatever comes next is a new stream: nothing retained, no phase carried over, no chunk boundaries of the old one
         m_base += m_buf_n;
         m_buf_n = 0;
         m_handled = m_base;
+        m_stream_start = m_base;
         m_pending_lts1 = -1;
+        m_phase = 0.0;
+        m_calls.clear();
         return out;
     }
 
@@ -358,7 +362,7 @@ namespace fun
             const b200rx_pass_frame &fr = frames[f];
             const int64_t lts1 = (int64_t)(m_base + fr.lts1);
             if (lts1 <= m_last_lts1) continue;
-            if (m_base > 0 && fr.lts1 < KEEP_BEFORE / 2 && lts1 != m_pending_lts1) continue;
+            if (m_base > m_stream_start && fr.lts1 < KEEP_BEFORE / 2 && lts1 != m_pending_lts1) continue;
             const uint8_t st = fr.status;
             if (st == B200RX_ST_TRUNCATED && f + 1 == nf) { // may still be arriving
                 pending_lts1 = lts1;

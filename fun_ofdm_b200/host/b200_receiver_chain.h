@@ -96,6 +96,7 @@ namespace fun
         bool reserve(size_t n);
         uint64_t m_base;                           // stream index of m_buf[0]
         uint64_t m_handled;                        // STS_END tags below this stream index have been examined
+        uint64_t m_stream_start;                   // stream index at which the current stream began (0, or where flush() cut)
         int64_t m_last_lts1;                       // LTS1 index of the last frame settled (-1: none)
         std::deque<uint64_t> m_calls;              // stream index at which each recent process_samples() call started
         int64_t m_pending_lts1;                    // LTS1 index of the frame still arriving (-1: none)

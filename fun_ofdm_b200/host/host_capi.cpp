@@ -48,6 +48,55 @@ API int b200host_rx_block_work(void *blk, const double *iq, const uint8_t *tags,
     return count;
 }
 
+API void *b200host_rx_block_new2(int device, unsigned max_frames, unsigned max_payload, unsigned depth, unsigned max_lag)
+{
+    fun::b200_rx *b = new fun::b200_rx(device, max_frames, max_payload, depth, max_lag);
+    if (!b->ok()) { delete b; return nullptr; }
+    return b;
+}
+
+// The block inside a chain, in native code: the tagged stream (iq, tags)[0, n) is cut into rounds of `chunk` samples,
+// each round's std::vector<tagged_sample> is built beforehand (in the reference it is timing_sync's output_buffer, swapped
+// into this block's input_buffer by receiver_chain.cpp:119 - no copy), then the timed loop swaps it in and calls work().
+// seconds[0] = the rounds, seconds[1] = rounds + flush.  Returns the number of payloads.
+API int b200host_rx_block_run(void *blk, const double *iq, const uint8_t *tags, long n, long chunk, uint8_t *payload_out,
+                              int stride, int32_t *len_out, int max_out, double *seconds)
+{
+    fun::b200_rx *b = static_cast<fun::b200_rx *>(blk);
+    std::vector<std::vector<fun::tagged_sample> > rounds;
+    for (long s = 0; s < n; s += chunk) {
+        const long len = n - s < chunk ? n - s : chunk;
+        rounds.push_back(std::vector<fun::tagged_sample>((size_t)len));
+        for (long i = 0; i < len; i++) {
+            rounds.back()[i].sample = std::complex<double>(iq[2 * (s + i)], iq[2 * (s + i) + 1]);
+            rounds.back()[i].tag = (fun::vector_tag)tags[s + i];
+        }
+    }
+    int count = 0;
+    auto take = [&](const std::vector<std::vector<unsigned char> > &out) {
+        for (size_t k = 0; k < out.size(); k++, count++) {
+            if (count >= max_out) continue;
+            int m = (int)out[k].size() < stride ? (int)out[k].size() : stride;
+            if (m) std::memcpy(payload_out + (size_t)count * stride, out[k].data(), m);
+            len_out[count] = (int32_t)out[k].size();
+        }
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t r = 0; r < rounds.size(); r++) {
+        b->input_buffer.swap(rounds[r]);
+        b->work();
+        take(b->output_buffer);
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    b->output_buffer.resize(0);
+    b->flush();
+    take(b->output_buffer);
+    const auto t2 = std::chrono::steady_clock::now();
+    seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+    seconds[1] = std::chrono::duration<double>(t2 - t0).count();
+    return count;
+}
+
 API void b200host_rx_block_counters(void *blk, uint64_t *out5)
 {
     fun::b200_rx::counters_t c = static_cast<fun::b200_rx *>(blk)->counters();

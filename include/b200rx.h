@@ -119,6 +119,11 @@ B200RX_API int b200rx_synchronize(b200rx_handle *h);
 #define B200RX_FMT_FC64 0
 #define B200RX_FMT_FC32 1
 #define B200RX_FMT_SC16 2
+/* The reference's own element type between timing_sync and fft_symbols: fun::tagged_sample (tagged_vector.h:82-94),
+ * { std::complex<double> sample; vector_tag tag; } = 24 bytes.  Accepted by the decode entry points (the tags are
+ * ignored there, lts1_index says where frames start) and by b200rx_pass_scan_tagged (which reads them); the raw-capture
+ * entry points do not take it - a tagged stream has been through frame_detector and timing_sync already. */
+#define B200RX_FMT_TAGGED_FC64 3
 B200RX_API int b200rx_set_sample_format(b200rx_handle *h, int format, double sc16_scale);
 
 /* Implementation knobs, per handle (nothing is read from the environment).  Results never depend on them; they select
@@ -284,6 +289,12 @@ B200RX_API int b200rx_pass_open(b200rx_handle *h);
 B200RX_API int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n_samples);
 B200RX_API int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frames, uint32_t frames_cap,
                                 b200rx_sync_result *res);
+/* Phase one for a stream that timing_sync has tagged already (fun::b200_rx, the block that replaces fft_symbols ..
+ * frame_decoder): the handle's sample format must be B200RX_FMT_TAGGED_FC64; a frame starts at every sample whose tag is
+ * LTS1 (fft_symbols.cpp:42-51) and extends to the next such sample or the end of the staged stream.  Same outputs as
+ * b200rx_pass_scan (res->n_events = LTS1 tags seen, res->overflow = those beyond max_frames); the structs are unpacked
+ * on the GPU, the host never walks them. */
+B200RX_API int b200rx_pass_scan_tagged(b200rx_handle *h, b200rx_pass_frame *frames, uint32_t frames_cap, b200rx_sync_result *res);
 B200RX_API int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload_out, uint32_t payload_stride,
                                   uint8_t *status, uint64_t *ticket);
 B200RX_API int b200rx_pass_poll(b200rx_handle *h, uint64_t ticket);

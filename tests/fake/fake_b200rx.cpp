@@ -61,6 +61,8 @@ struct b200rx_handle {
     std::string error;
     // two-phase passes: the staged capture and what the reference made of it
     std::vector<double> pass_iq;
+    std::vector<uint8_t> pass_raw; // tagged passes: the 24-byte structs as put
+    int fmt = B200RX_FMT_FC64;
     std::vector<uint8_t> pass_payload, pass_status;
     std::vector<uint16_t> pass_len;
     uint32_t pass_frames = 0;
@@ -149,11 +151,54 @@ int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n, double, uint8_t
 // ---- two-phase passes: scan = the same capture logic, decode = hand out what the scan already computed ----
 int b200rx_set_pipeline_depth(b200rx_handle *, uint32_t) { return B200RX_OK; }
 int b200rx_host_is_pinned(const void *) { return 0; }
-int b200rx_pass_open(b200rx_handle *h) { h->pass_iq.clear(); h->pass_frames = 0; return B200RX_OK; }
+int b200rx_set_sample_format(b200rx_handle *h, int fmt, double) { h->fmt = fmt; return B200RX_OK; }
+int b200rx_pass_open(b200rx_handle *h) { h->pass_iq.clear(); h->pass_raw.clear(); h->pass_frames = 0; return B200RX_OK; }
 int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n)
 {
+    if (h->fmt == B200RX_FMT_TAGGED_FC64) {
+        const uint8_t *p = (const uint8_t *)iq;
+        h->pass_raw.insert(h->pass_raw.end(), p, p + 24 * n);
+        return B200RX_OK;
+    }
     const double *p = (const double *)iq;
     h->pass_iq.insert(h->pass_iq.end(), p, p + 2 * n);
+    return B200RX_OK;
+}
+// a stream timing_sync has tagged: frames start at the LTS1 tags, each window through the reference's four blocks
+int b200rx_pass_scan_tagged(b200rx_handle *h, b200rx_pass_frame *frames, uint32_t cap, b200rx_sync_result *res)
+{
+    memset(res, 0, sizeof(*res));
+    const uint32_t mf = h->lim.max_frames, stride = h->lim.max_payload_bytes ? h->lim.max_payload_bytes : 1;
+    h->pass_payload.assign((size_t)mf * stride, 0);
+    h->pass_status.assign(mf, B200RX_ST_NO_FRAME);
+    h->pass_len.assign(mf, 0);
+    const uint64_t n = h->pass_raw.size() / 24;
+    std::vector<double> iq(2 * n);
+    std::vector<uint64_t> starts;
+    for (uint64_t i = 0; i < n; i++) {
+        memcpy(&iq[2 * i], &h->pass_raw[24 * i], 16);
+        int32_t tag;
+        memcpy(&tag, &h->pass_raw[24 * i + 16], 4);
+        if (tag == 4) starts.push_back(i);
+    }
+    uint32_t nf = 0;
+    for (size_t k = 0; k < starts.size() && nf < mf; k++, nf++) {
+        const uint64_t a = starts[k], e = k + 1 < starts.size() ? starts[k + 1] : n;
+        uint8_t rate = 0;
+        decode_window(iq.data() + 2 * a, (uint32_t)(e - a), h->lim.max_payload_bytes, h->pass_payload.data() + (size_t)nf * stride,
+                      &h->pass_len[nf], &rate, &h->pass_status[nf], false);
+        if (nf < cap) {
+            frames[nf].lts1 = a;
+            frames[nf].avail = (uint32_t)(e - a);
+            frames[nf].length = h->pass_len[nf];
+            frames[nf].rate = rate;
+            frames[nf].status = h->pass_status[nf] == B200RX_ST_CRC_FAIL ? (uint8_t)B200RX_ST_OK : h->pass_status[nf];
+        }
+    }
+    h->pass_frames = nf;
+    res->n_events = (uint32_t)starts.size();
+    res->n_frames = nf;
+    res->overflow = (uint32_t)(starts.size() - nf);
     return B200RX_OK;
 }
 int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frames, uint32_t cap, b200rx_sync_result *res)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class Block:
-    def __init__(self, max_frames=64, max_payload=4095, lib_path=None):
+    def __init__(self, max_frames=64, max_payload=4095, lib_path=None, depth=None, max_lag=3):
         self.lib = C.CDLL(lib_path or os.path.join(ROOT, "fun_ofdm_b200", "lib", "libb200host.so"))
         self.lib.b200host_rx_block_new.restype = C.c_void_p
         self.lib.b200host_rx_block_new.argtypes = [C.c_int, C.c_uint, C.c_uint]
@@ -20,8 +20,29 @@ class Block:
                                                     C.c_int, C.c_void_p, C.c_int]
         self.lib.b200host_rx_block_delete.argtypes = [C.c_void_p]
         self.lib.b200host_rx_block_counters.argtypes = [C.c_void_p, C.c_void_p]
-        self.h = self.lib.b200host_rx_block_new(0, max_frames, max_payload)
+        self.lib.b200host_rx_block_new2.restype = C.c_void_p
+        self.lib.b200host_rx_block_new2.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+        self.lib.b200host_rx_block_run.restype = C.c_int
+        self.lib.b200host_rx_block_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_int,
+                                                   C.c_void_p, C.c_int, C.c_void_p]
+        if depth is None:
+            self.h = self.lib.b200host_rx_block_new(0, max_frames, max_payload)
+        else:
+            self.h = self.lib.b200host_rx_block_new2(0, max_frames, max_payload, depth, max_lag)
         assert self.h, "b200_rx block could not be created (no GPU?)"
+
+    def run(self, samples, tags, chunk, max_out=4096, stride=4095):
+        """All rounds + flush in native code (host_capi.cpp: b200host_rx_block_run): (payloads, seconds of the rounds,
+        seconds including the flush); the per-round std::vector<tagged_sample> are built before the clock starts."""
+        iq = np.ascontiguousarray(samples, dtype=np.complex128).view(np.float64)
+        tags = np.ascontiguousarray(tags, dtype=np.uint8)
+        payload = np.zeros((max_out, stride), np.uint8)
+        length = np.zeros(max_out, np.int32)
+        sec = np.zeros(2, np.float64)
+        n = self.lib.b200host_rx_block_run(self.h, iq.ctypes.data, tags.ctypes.data, len(tags), chunk, payload.ctypes.data, stride,
+                                           length.ctypes.data, max_out, sec.ctypes.data)
+        assert n <= max_out
+        return [bytes(payload[i, : length[i]]) for i in range(n)], float(sec[0]), float(sec[1])
 
     def work(self, samples, tags, flush=False, max_out=512, stride=4095):
         iq = np.ascontiguousarray(samples, dtype=np.complex128).view(np.float64)
@@ -101,3 +122,25 @@ def test_block_genie_tags_and_frame_cut_short(ref):
     blk.close()
     assert got == want == [pl2]
     assert c["abandoned"] == 1 and c["ok"] == 1
+
+
+@pytest.mark.parametrize("depth,lag", [(1, 0), (4, 3), (8, 7)])
+def test_block_pipelined_rounds_native_loop(ref, depth, lag):
+    """The block inside the reference's round structure (input_buffer swapped in, work(), output_buffer read), native loop,
+    with 1, 4 and 8 passes in flight: the tagged_sample structs go to the GPU as they are (24 bytes each, tags found on
+    the device); payload sequence = the reference's four blocks on the same tagged stream."""
+    rng = np.random.default_rng(808 + depth)
+    rates = [int(r) for r in rng.integers(0, 11, 40)]
+    lengths = [int(v) for v in rng.integers(0, 1000, 40)]
+    x, payloads = _stream(ref, rng, rates, lengths, 24, gap=500)
+    for chunk in (4096, 30000):
+        samples, tags = ref.sync(x, chunk=chunk)
+        n_whole = (len(tags) // chunk) * chunk  # whole rounds only (DESIGN.md section 9: the reference's double delivery)
+        samples, tags = samples[:n_whole], tags[:n_whole]
+        want = ref.hotpath_stream(samples, tags, chunk=chunk)
+        blk = Block(max_frames=128, depth=depth, max_lag=lag)
+        got, t_rounds, t_all = blk.run(samples, tags, chunk)
+        c = blk.counters()
+        blk.close()
+        assert got == want, (depth, lag, chunk, len(got), len(want), c)
+        assert len(got) >= 25 and c["ok"] == len(got), c

@@ -247,3 +247,17 @@ def test_receiver_wrapper_callback_pause_resume(ref):
     got = [bytes(pl[i, : ln[i]]) for i in range(n)]
     assert got == want, (len(got), len(want))
     assert paused.value == 0
+
+
+def test_flush_starts_a_new_stream(ref):
+    """After flush() the chain behaves like a fresh one: a frame that starts within the first samples of the next stream
+    is found (a retained buffer's first 256 samples are skipped only when the stream did not start there)."""
+    data = bytes(range(200)) * 3
+    frame = ref.build_frame(data, 8)
+    x = np.concatenate([np.tile(frame, 6), np.zeros(3 * len(frame), complex)])
+    want = _reference_chain(ref, x, 4096)
+    ch = Chain()
+    first, _, _ = ch.run(x, 4096)
+    second, _, _ = ch.run(x, 4096)
+    ch.close()
+    assert first == want and second == want and len(want) == 6
