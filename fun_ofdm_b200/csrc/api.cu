@@ -775,6 +775,8 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     CU(h, cudaMemcpyAsync(S.d_lts1, lts1_index, n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CU(h, cudaMemcpyAsync(S.d_avail, avail, n_frames * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CU(h, cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long), s));
+    if (pl_bytes) CU(h, cudaMemsetAsync(S.d_payload, 0, pl_bytes, s)); // bytes behind a frame's LENGTH reach the caller as zeros,
+                                                                        // not as what an earlier call left in the staging
     const OutPtrs o{payload_out ? S.d_payload : nullptr, payload_stride, S.d_len, S.d_rate, S.d_status};
     auto finish = [&](cudaStream_t last) -> int {
         CU(h, cudaEventRecord(S.done, last));
@@ -1071,6 +1073,7 @@ int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n_samples, double 
         h->hs[0].d_payload_cap = pl_cap;
     }
     if (iq_bytes) CU(h, cudaMemcpyAsync(h->hs[0].d_iq, iq, iq_bytes, cudaMemcpyHostToDevice, s));
+    if (pl_cap) CU(h, cudaMemsetAsync(h->hs[0].d_payload, 0, pl_cap, s));
     const int li = h->depth > 1 ? (int)(h->call_idx % h->depth) : 0; // scratch set the next call uses
     rc = b200rx_receive_dev(h, h->hs[0].d_iq, n_samples, phase_in, payload_out ? h->hs[0].d_payload : nullptr, payload_stride, h->hs[0].d_len,
                             h->hs[0].d_rate, h->hs[0].d_status, nullptr, nullptr, res);
@@ -1345,6 +1348,7 @@ int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload
     }
     memcpy(P.h_select, select, n);
     CU(h, cudaMemcpyAsync(P.d_select, P.h_select, n, cudaMemcpyHostToDevice, s));
+    if (payload_out) CU(h, cudaMemsetAsync(P.d_payload + (size_t)lo * payload_stride, 0, (size_t)(hi - lo) * payload_stride, s));
     CU(h, cudaMemsetAsync(h->counters, 0, 8 * sizeof(unsigned long long), s));
     // A pass holds a handful of frames unless the caller hands over a long capture; what it owes the caller is a short
     // tail behind the scan: the generation-2 ACS kernel with 16 lanes per frame takes 0.7 ms for 12 096 dependent steps

@@ -118,6 +118,7 @@ def test_block_genie_tags_and_frame_cut_short(ref):
     got = []
     for s in range(0, len(x), 1000):
         got += blk.work(x[s: s + 1000], tags[s: s + 1000])
+    got += blk.work(np.zeros(1, complex), np.zeros(1, np.uint8), flush=True)  # payloads surface up to max_lag rounds late
     c = blk.counters()
     blk.close()
     assert got == want == [pl2]
