@@ -20,6 +20,50 @@ from oracle import bind  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+FAIL_SNR = [3, 5, 7, 6, 8, 10, 12, 14, 16, 20, 22]  # dB at which roughly half of the 1500-byte frames fail, per rate
+
+
+def big_cases():
+    """(rate, length, snr_db, seed) of the full-size fixtures: every rate x {1500, 4095} bytes x {45 dB, 30 dB, the SNR at
+    which about half the frames fail}.  45 dB stands in for "clean": exactly noiseless frames put the constellation points
+    ON the demapper's truncation boundaries (qam.h:112), where the last bit of the FFT's summation order decides a soft
+    value - FFTW, the checker's shim FFT and any other correct DFT differ there (known deviations)."""
+    cases = []
+    for rate in range(11):
+        for length in (1500, 4095):
+            for k, snr in enumerate((45.0, 30.0, float(FAIL_SNR[rate]))):
+                cases.append((rate, length, snr, 7000 + 100 * rate + 10 * (length == 4095) + k))
+    return cases
+
+
+def big_frame_samples(rate, length, snr, seed):
+    """The frame as the product's host generator builds it (fun_ofdm_b200/host/txgen.cpp: counter-based noise, the same
+    bits on every machine; pinned against frame_builder by the tests).  Full-size frames are not stored - 66 of them are
+    33 MB of samples - but regenerated from these parameters; the fixture keeps the SHA-256 of the sample bytes, so a test
+    that regenerates them knows it decodes exactly what the reference decoded when the fixture was made."""
+    from fun_ofdm_b200 import tx
+    payload = np.random.default_rng(seed).integers(0, 256, length, dtype=np.uint8)
+    c = tx.build_corpus([payload.tobytes()], [rate], snr_db=snr, lead_in=0, seed=seed, threads=1)
+    return payload, np.ascontiguousarray(c["iq"][int(c["lts1"][0]): int(c["lts1"][0]) + int(c["avail"][0])])
+
+
+def big_frames(ref):
+    import hashlib
+    out, meta = {}, []
+    for k, (rate, length, snr, seed) in enumerate(big_cases()):
+        payload, win = big_frame_samples(rate, length, snr, seed)
+        d = ref.decode_frame(win)
+        out["sha256_%d" % k] = np.frombuffer(hashlib.sha256(win.tobytes()).digest(), dtype=np.uint8)
+        out["descrambled_%d" % k] = d.descrambled if d.descrambled is not None else np.zeros(0, np.uint8)
+        meta.append([rate, length, -1 if snr is None else int(round(snr)), seed, int(d.hdr_ok), d.hdr_field, int(d.rate_valid),
+                     d.rate, d.length, d.nsym, int(d.crc_ok), int(d.crc_ok and bytes(d.payload) == payload.tobytes())])
+    out["meta"] = np.array(meta, dtype=np.int64)
+    path = os.path.join(HERE, "big_frames.npz")
+    np.savez_compressed(path, **out)
+    m = out["meta"]
+    print("wrote", path, os.path.getsize(path), "crc ok %d of %d, header ok %d" % (m[:, 10].sum(), len(m), m[:, 4].sum()))
+
+
 def main():
     ref = bind.ref()
     rng = np.random.default_rng(20261017)
@@ -90,6 +134,7 @@ def main():
                      int(d.rate_valid), d.rate, d.length, d.nsym, int(d.crc_ok), d.n_vectors])
     frames["meta"] = np.array(meta, dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "frames.npz"), **frames)
+    big_frames(ref)
     print("wrote", os.path.join(HERE, "stage_kat.npz"), os.path.getsize(os.path.join(HERE, "stage_kat.npz")),
           os.path.join(HERE, "frames.npz"), os.path.getsize(os.path.join(HERE, "frames.npz")))
     print(np.array(meta))

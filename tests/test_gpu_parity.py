@@ -310,3 +310,46 @@ def test_pipelined_calls_match_sequential(ref, rx_factory):
     rx.set_pipeline_depth(1)
     again = gpu_decode(rx, corpora[0], taps=False)
     assert np.array_equal(again["payload"], seq[0]["payload"]) and np.array_equal(again["status"], seq[0]["status"])
+
+
+def test_full_size_fixture_frames(rx_factory):
+    """The committed full-size fixtures (tests/golden/big_frames.npz: all 11 rates x {1500, 4095} bytes x {45 dB, 30 dB,
+    failing SNR}, decoded by the compiled reference when the fixture was made): status, rate, LENGTH, the descrambled
+    bytes of every frame (CRC failures included) and the payloads must be identical.  Needs no reference on the box."""
+    from test_oracle_golden import BIG, big_frame
+    rx = rx_factory(66, 4095)
+    rows, wins = [], []
+    for k in range(66):
+        row, payload, win = big_frame(k)
+        rows.append((row, payload))
+        wins.append(win)
+    lts1 = np.cumsum([0] + [len(w) for w in wins[:-1]]).astype(np.uint64)
+    corpus = dict(iq=np.concatenate(wins), lts1=lts1, avail=np.array([len(w) for w in wins], np.uint32))
+    dev = torch.device("cuda:0")
+    n = 66
+    payload_t = torch.zeros((n, 4095), dtype=torch.uint8, device=dev)
+    length = torch.zeros(n, dtype=torch.int16, device=dev)
+    rate = torch.zeros(n, dtype=torch.uint8, device=dev)
+    status = torch.full((n,), 99, dtype=torch.uint8, device=dev)
+    decoded = torch.zeros((n, rx.max_steps // 8 + 8), dtype=torch.uint8, device=dev)
+    rx.decode_batch_dev(torch.from_numpy(corpus["iq"].view(np.float64)).to(dev), torch.from_numpy(corpus["lts1"]).to(dev),
+                        torch.from_numpy(corpus["avail"]).to(dev), payload_t, length, rate, status, dict(decoded=decoded))
+    rx.synchronize()
+    st, ln, rt, pl = status.cpu().numpy(), length.cpu().numpy().astype(np.uint16), rate.cpu().numpy(), payload_t.cpu().numpy()
+    # the descrambler (ppdu.cpp:255-264) on the tapped Viterbi output, to compare failed frames byte for byte
+    scr, state = [], 93
+    for _ in range(127):
+        fb = ((state >> 6) & 1) ^ ((state >> 3) & 1)
+        scr.append(fb)
+        state = ((state << 1) & 0x7E) | fb
+    scr = np.array(scr, np.uint8)
+    dec = decoded.cpu().numpy()
+    for k, (row, payload) in enumerate(rows):
+        r, le, snr, seed, hdr_ok, field, rate_valid, drate, dlen, nsym, crc_ok, pl_equal = row
+        assert hdr_ok and st[k] == (0 if crc_ok else 3), (k, row, st[k])
+        assert rt[k] == drate and ln[k] == dlen, (k, row)
+        want = BIG["descrambled_%d" % k]
+        got = dec[k, : len(want)] ^ scr[np.arange(len(want)) % 127]
+        assert np.array_equal(got, want), (k, row)
+        if crc_ok:
+            assert (bytes(pl[k, :dlen]) == payload.tobytes()) == bool(pl_equal), (k, row)

@@ -2,6 +2,7 @@
 the compiled reference (tests/golden/make_golden.py), and — where oracle/_ref exists — against the
 reference itself on fresh random inputs.  Integer outputs bit-exact; fp64 outputs within 1e-12."""
 import os
+import sys
 import zlib
 
 import numpy as np
@@ -101,3 +102,41 @@ def test_batch_entry_point_of_port(port):
         assert (status[k] == 0) == bool(hdr_ok and crc_ok)
         if status[k] == 0:
             assert bytes(payload[k, :dlen]) == bytes(FRAMES["payload_%d" % k])
+
+
+# ---- full-size frames: every rate x {1500, 4095} bytes x {45 dB, 30 dB, the SNR where about half the frames fail} ----
+BIG = np.load(os.path.join(HERE, "golden", "big_frames.npz"))
+
+
+def big_frame(k):
+    """Regenerates fixture frame k from its parameters (tests/golden/make_golden.py: big_frame_samples) and checks the
+    SHA-256 of the samples against the one recorded when the reference decoded them.  Returns (meta row, payload, window)."""
+    import hashlib
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_golden import big_frame_samples
+    row = [int(v) for v in BIG["meta"][k]]
+    rate, length, snr, seed = row[:4]
+    payload, win = big_frame_samples(rate, length, None if snr < 0 else float(snr), seed)
+    assert hashlib.sha256(win.tobytes()).digest() == bytes(BIG["sha256_%d" % k]), \
+        "fixture %d: the regenerated samples differ from the ones the reference decoded" % k
+    return row, payload, win
+
+
+def test_big_fixture_covers_every_rate_and_both_verdicts():
+    m = BIG["meta"]
+    assert len(m) == 66 and set(m[:, 0]) == set(range(11)) and set(m[:, 1]) == {1500, 4095}
+    assert m[:, 4].all()                      # every header decodes
+    assert (m[:, 10] == 0).sum() >= 5         # CRC failures are in the set ...
+    assert m[:, 10].sum() >= 44               # ... and so are full-size successes (all clean and 30 dB frames)
+
+
+@pytest.mark.parametrize("k", range(66))
+def test_port_matches_reference_on_full_size_frames(port, k):
+    row, payload, win = big_frame(k)
+    rate, length, snr, seed, hdr_ok, field, rate_valid, drate, dlen, nsym, crc_ok, pl_equal = row
+    d = port.decode_frame(win)
+    assert (d.hdr_ok, d.hdr_field, d.rate_valid) == (bool(hdr_ok), field, bool(rate_valid))
+    assert (d.rate, d.length, d.nsym, d.crc_ok) == (drate, dlen, nsym, bool(crc_ok))
+    assert np.array_equal(d.descrambled, BIG["descrambled_%d" % k])
+    if crc_ok:
+        assert (bytes(d.payload) == payload.tobytes()) == bool(pl_equal)
