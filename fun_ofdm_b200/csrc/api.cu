@@ -582,6 +582,7 @@ int launch_range(b200rx_handle *h, const Tuning &tn, cudaStream_t s, uint32_t of
     fa.rot = rot_dev ? rot_dev + off : nullptr;
     fa.n_live = n_live_dev;
     fa.select = select_dev ? select_dev + off : nullptr;
+    fa.sm_count = tn.sm_count;
     if (dbg) {
         fa.dbg_eq = dbg->equalized ? reinterpret_cast<double2 *>(dbg->equalized) + (size_t)off * dbg->eq_vectors * 48 : nullptr;
         fa.dbg_eq_vectors = dbg->eq_vectors;

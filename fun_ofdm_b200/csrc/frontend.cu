@@ -34,17 +34,18 @@ constexpr int ERASURE_AT = 288;
 // Per rate: for trellis step t of an OFDM symbol the two soft-bit indices (demodulator order) it consumes,
 // i.e. depuncture (puncturer.cpp:94-118) composed with deinterleave (interleaver.cpp:31-37); ERASURE_AT marks a
 // re-inserted erasure (value 127).  Filled by upload_frontend_tables from step_index_pair() below.
-__constant__ uint32_t c_step_idx[11][216];
+__device__ uint32_t c_step_idx[11][216]; // global memory, not __constant__: every thread reads its own entry (a constant
+                                         // bank serves one address per cycle, 32 replays per warp-wide load)
 
 // Inverse of c_step_idx for the data kernel: soft byte i (demodulator order) of an OFDM symbol -> its byte offset 2 * t + slot
 // in the symbol's run of depunctured soft-symbol pairs; the offsets no soft byte maps to are the re-inserted erasures.
-__constant__ uint16_t c_scatter[11][288];
+__device__ uint16_t c_scatter[11][288];
 // QAM<N>::decode (qam.h:110-125) of one axis as a table: soft bits of pt = clamp(u, -320, 320), byte i = bit i, for
 // N = 1, 2, 3 (beyond +-320 every bit has reached its final value 0 or 255).
 constexpr int SOFT_TAB_HALF = 320, SOFT_TAB_N = 2 * SOFT_TAB_HALF + 1;
-__constant__ uint32_t c_soft_tab[3][SOFT_TAB_N];
+__device__ uint32_t c_soft_tab[3][SOFT_TAB_N];
 
-__constant__ double2 c_twiddle[64];  // exp(-2 pi i k / 64)
+__device__ double2 c_twiddle[64];    // exp(-2 pi i k / 64)
 __constant__ int8_t c_polarity[127]; // pilot polarity sequence (phase_tracker.cpp:23-32)
 
 // LTS_FREQ_DOMAIN (preamble.h:363-429; IEEE 802.11a 17.3.3 L_{-26..26}), index s <-> subcarrier s - 32.
@@ -378,6 +379,9 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(
 // One CTA (4 warps) per frame; no barrier after the setup.
 // ------------------------------------------------------------------------------------------------
 constexpr int DK_WARPS = 4;
+#ifndef DK_MIN_BLOCKS
+#define DK_MIN_BLOCKS 5 // CTAs per SM the register allocation aims at (5: 96 registers, no spills)
+#endif
 constexpr int DK_TR_STRIDE = 9;      // double2 per transposition row (8 + 1: 16-byte accesses of 8 lanes hit 8 bank groups)
 constexpr int DK_PAIR_BYTES = 432;   // 2 * max dbps
 
@@ -531,7 +535,7 @@ __device__ __forceinline__ void data_symbols(const DataArgs &a, int frame, const
 }
 
 template <bool ROT, int FMT, bool DBG>
-__global__ void __launch_bounds__(DK_WARPS * 32) data_kernel(DataArgs a)
+__global__ void __launch_bounds__(DK_WARPS * 32, DK_MIN_BLOCKS) data_kernel(DataArgs a)
 {
     __shared__ double2 s_hinv[64];      // [k2][r] = H^-1 of DFT bin r + 8 k2 (natural DFT order): lane r reads [k2][r], conflict-free
     __shared__ double2 s_tw[8][8];      // [k1][r] = W64^(r k1)
@@ -541,32 +545,13 @@ __global__ void __launch_bounds__(DK_WARPS * 32) data_kernel(DataArgs a)
     __shared__ uint16_t s_scatter[288];
     __shared__ uint32_t s_soft[SOFT_TAB_N];
 
-    const int frame = blockIdx.x;
-    const FrameDesc d = a.desc[frame];
-    if (d.status != B200RX_ST_OK || d.n_steps == 0) return;
+    // Persistent CTAs: each takes every gridDim.x-th frame, so the tables (672 words) are staged once per CTA and again
+    // only when the rate changes, not once per frame (ncu, one CTA per frame: 18 % of the kernel's stall samples sat on
+    // the stores of this staging, waiting for divergent constant-bank reads).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = lane >> 3, r = lane & 7;
-    const int bpsc = rate_row(d.rate).bpsc;
-    const int tab = bpsc <= 2 ? 0 : (bpsc == 4 ? 1 : 2);
-
-    if (tid < 64) {
-        s_hinv[tid] = a.hinv[(size_t)frame * 64 + ((tid + 32) & 63)]; // a.hinv is in the reference's shifted order
-        s_tw[tid >> 3][tid & 7] = c_twiddle[((tid >> 3) * (tid & 7)) & 63];
-    }
-    for (int i = tid; i < 288; i += DK_WARPS * 32) s_scatter[i] = c_scatter[d.rate][i];
-    for (int i = tid; i < SOFT_TAB_N; i += DK_WARPS * 32) s_soft[i] = c_soft_tab[tab][i];
-    for (int i = tid; i < DK_WARPS * 4 * DK_PAIR_BYTES / 4; i += DK_WARPS * 32)
-        reinterpret_cast<uint32_t *>(&s_pairs[0][0])[i] = 0x7F7F7F7Fu; // erasures (puncturer.cpp:98): data bytes are overwritten per symbol
-    __syncthreads();
-
-    const Window win{a.iq, a.lts1[frame], a.scale};
-    RotCtx rc{};
-    if constexpr (ROT) {
-        const FrameRot fr = a.rot[frame];
-        rc.rn = fr.rot_new;
-        rc.ro = fr.rot_old;
-        rc.from = (int64_t)fr.from - (int64_t)win.p;
-    }
+    if (tid < 64) s_tw[tid >> 3][tid & 7] = c_twiddle[((tid >> 3) * (tid & 7)) & 63];
+    int cur_rate = -1, cur_tab = -1;
     double2 *tr_row = &s_tr[warp][q][r][0];
     const double2 *tr_col = &s_tr[warp][q][0][r];
     double2 *pil = &s_pil[warp][q][0];
@@ -574,11 +559,38 @@ __global__ void __launch_bounds__(DK_WARPS * 32) data_kernel(DataArgs a)
     const double2 *tw_r = &s_tw[0][r];
     const uint32_t *soft_tab = s_soft + SOFT_TAB_HALF;
     uint8_t *tile = &s_pairs[warp][0];
-    switch (bpsc) {
-        case 1: data_symbols<ROT, FMT, DBG, 1>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
-        case 2: data_symbols<ROT, FMT, DBG, 2>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
-        case 4: data_symbols<ROT, FMT, DBG, 4>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
-        default: data_symbols<ROT, FMT, DBG, 6>(a, frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+    for (uint32_t frame = blockIdx.x; frame < a.n_frames; frame += gridDim.x) {
+        const FrameDesc d = a.desc[frame];
+        if (d.status != B200RX_ST_OK || d.n_steps == 0) continue; // the same for every thread of the CTA
+        const int bpsc = rate_row(d.rate).bpsc;
+        const int tab = bpsc <= 2 ? 0 : (bpsc == 4 ? 1 : 2);
+        __syncthreads(); // every warp has finished the previous frame
+        if (tid < 64) s_hinv[tid] = a.hinv[(size_t)frame * 64 + ((tid + 32) & 63)]; // a.hinv is in the reference's shifted order
+        if ((int)d.rate != cur_rate) {
+            for (int i = tid; i < 288; i += DK_WARPS * 32) s_scatter[i] = c_scatter[d.rate][i];
+            if (tab != cur_tab)
+                for (int i = tid; i < SOFT_TAB_N; i += DK_WARPS * 32) s_soft[i] = c_soft_tab[tab][i];
+            for (int i = tid; i < DK_WARPS * 4 * DK_PAIR_BYTES / 4; i += DK_WARPS * 32)
+                reinterpret_cast<uint32_t *>(&s_pairs[0][0])[i] = 0x7F7F7F7Fu; // erasures (puncturer.cpp:98): data bytes are overwritten per symbol
+            cur_rate = d.rate;
+            cur_tab = tab;
+        }
+        __syncthreads();
+
+        const Window win{a.iq, a.lts1[frame], a.scale};
+        RotCtx rc{};
+        if constexpr (ROT) {
+            const FrameRot fr = a.rot[frame];
+            rc.rn = fr.rot_new;
+            rc.ro = fr.rot_old;
+            rc.from = (int64_t)fr.from - (int64_t)win.p;
+        }
+        switch (bpsc) {
+            case 1: data_symbols<ROT, FMT, DBG, 1>(a, (int)frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+            case 2: data_symbols<ROT, FMT, DBG, 2>(a, (int)frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+            case 4: data_symbols<ROT, FMT, DBG, 4>(a, (int)frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+            default: data_symbols<ROT, FMT, DBG, 6>(a, (int)frame, d, win, rc, tr_row, tr_col, pil, hinv_r, tw_r, soft_tab, s_scatter, tile, lane, warp); break;
+        }
     }
 }
 
@@ -633,7 +645,8 @@ cudaError_t launch_frontend_data(const FrontendArgs &a, cudaStream_t s)
     d.iq = a.iq; d.scale = a.scale; d.iq_samples = a.iq_samples; d.lts1 = a.lts1; d.n_frames = a.n_frames; d.desc = a.desc;
     d.hinv = a.hinv_out; d.pairs = reinterpret_cast<uint8_t *>(a.bm); d.pair_stride = (uint64_t)a.bm_stride * 4; d.rot = a.rot;
     d.dbg_eq = a.dbg_eq; d.dbg_eq_vectors = a.dbg_eq_vectors; d.dbg_depunct = a.dbg_depunct; d.dbg_depunct_stride = a.dbg_depunct_stride;
-    const dim3 grid(a.n_frames), block(DK_WARPS * 32);
+    const uint32_t resident = (uint32_t)(a.sm_count > 0 ? a.sm_count : 148) * DK_MIN_BLOCKS; // persistent grid: what the GPU holds at once
+    const dim3 grid(a.n_frames < resident ? a.n_frames : resident), block(DK_WARPS * 32);
     const bool dbg = a.dbg_eq != nullptr || a.dbg_depunct != nullptr;
 #define DK_LAUNCH(ROTV, FMTV) do { if (dbg) data_kernel<ROTV, FMTV, true><<<grid, block, 0, s>>>(d); \
                                    else data_kernel<ROTV, FMTV, false><<<grid, block, 0, s>>>(d); } while (0)

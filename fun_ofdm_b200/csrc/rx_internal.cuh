@@ -229,6 +229,7 @@ struct FrontendArgs {
     double2 *hinv_out;       // [n_frames][64] inverse channel of each frame (shifted order), or null
     const FrameRot *rot;     // per frame, or null: samples are used as they are
     const uint32_t *n_live;  // device count of valid frames (slots beyond it become B200RX_ST_NO_FRAME), or null
+    int sm_count;            // multiprocessors of the device (persistent grids); 0 = 148
     const uint8_t *select;   // per frame, or null: frames with select[f] == 0 are skipped (B200RX_ST_NO_FRAME; b200rx_pass_decode)
     // taps (may be null)
     double2 *dbg_eq;
