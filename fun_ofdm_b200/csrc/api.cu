@@ -434,13 +434,14 @@ int b200rx_set_tuning(b200rx_handle *h, const char *key, int64_t value)
 }
 
 int b200rx_set_receive_origins(b200rx_handle *h, const int64_t *origins, uint32_t n)
-{
+try {
     if (!h || (n && !origins)) return B200RX_E_ARG;
     for (uint32_t i = 1; i < n; i++)
         if (origins[i] < origins[i - 1]) return fail(h, B200RX_E_ARG, "b200rx_set_receive_origins: origins must ascend");
     h->origins.assign(origins, origins + n);
     return B200RX_OK;
 }
+catch (...) { return B200RX_E_NOMEM; } // std::bad_alloc must not cross the C boundary
 
 int b200rx_synchronize(b200rx_handle *h)
 {
@@ -739,7 +740,7 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
                         const uint64_t *lts1_index, const uint32_t *avail, uint32_t n_frames,
                         uint8_t *payload_out, uint32_t payload_stride,
                         uint16_t *payload_len, uint8_t *rate_out, uint8_t *status, uint64_t *ticket)
-{
+try {
     if (!h) return B200RX_E_ARG;
     if (!iq || !lts1_index || !avail || !status || !ticket) return fail(h, B200RX_E_ARG, "b200rx_submit_batch: null argument");
     if (n_frames > h->limits.max_frames) return fail(h, B200RX_E_ARG, "b200rx_submit_batch: n_frames exceeds max_frames");
@@ -884,6 +885,7 @@ int b200rx_submit_batch(b200rx_handle *h, const void *iq, uint64_t iq_samples,
     // every chunk's kernels are ordered before its copies on d2h_stream, so its tail is the end of the call
     return finish(h->d2h_stream);
 }
+catch (...) { return B200RX_E_NOMEM; } // std::bad_alloc must not cross the C boundary
 
 namespace {
 
@@ -1486,7 +1488,7 @@ int b200rx_viterbi_batch_dev(b200rx_handle *h, const uint8_t *symbols_dev, uint6
 }
 
 int b200rx_profile_begin(b200rx_handle *h, uint32_t slots)
-{
+try {
     if (!h) return B200RX_E_ARG;
     if (slots > 65536) return fail(h, B200RX_E_ARG, "b200rx_profile_begin: at most 65536 slots");
     CU(h, cudaSetDevice(h->device));
@@ -1497,6 +1499,7 @@ int b200rx_profile_begin(b200rx_handle *h, uint32_t slots)
     h->ring_used = 0;
     return B200RX_OK;
 }
+catch (...) { return B200RX_E_NOMEM; } // std::bad_alloc must not cross the C boundary
 
 int b200rx_profile_read(b200rx_handle *h, uint32_t *calls, float *frontend_ms, float *viterbi_ms, float *traceback_ms)
 {

@@ -219,7 +219,7 @@ int b200rx_group_create(const int *devices, uint32_t n_devices, const b200rx_lim
         const int r = g->workers[i]->wait();
         if (r != B200RX_OK && rc == B200RX_OK) {
             rc = r;
-            char d[600];
+            char d[400];
             snprintf(d, sizeof(d), "device %d: %s", devices[i], err[i].data());
             gfail(nullptr, r, "b200rx_group_create", d);
         }
@@ -345,7 +345,7 @@ int b200rx_group_decode_batch_dev(b200rx_group *g, const void *const *iq_dev, co
 
 int b200rx_gather_status(b200rx_group *g, const uint8_t *const *status_dev, uint32_t frames_per_device,
                          uint8_t *const *gathered_dev, uint64_t *counters_sum)
-{
+try {
     if (!g) return B200RX_E_ARG;
     int rc = ensure_comms(g);
     if (rc != B200RX_OK) return rc;
@@ -381,5 +381,6 @@ int b200rx_gather_status(b200rx_group *g, const uint8_t *const *status_dev, uint
         for (int k = 0; k < 4; k++) counters_sum[k] = g->sum_host[k];
     return B200RX_OK;
 }
+catch (...) { return B200RX_E_NOMEM; }
 
 } // extern "C"

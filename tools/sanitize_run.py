@@ -132,6 +132,35 @@ def main():
     res = rx.sync_dev(d_x, tags=tags)
     print("sync_dev: %s" % res)
     rx.close()
+
+    # ---- two-phase passes through the host adapters (pack_pass_kernel, tag_find / tag_frames kernels, select mask,
+    # tagged sample format), a group of one device with the NCCL gather ----
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_chain import Chain
+    from test_gpu_block import Block
+    xs = np.concatenate([x, x * 0.5, np.zeros(4096, complex)])
+    ch = Chain(max_frames=64, max_payload=400, depth=3, max_lag=2)
+    got_chain, _, _ = ch.run(xs, 4096, max_out=64, stride=400)
+    ch.close()
+    print("b200_receiver_chain (passes): %d payloads" % len(got_chain))
+    tg = np.zeros(len(corpus["iq"]), np.uint8)
+    tg[corpus["lts1"].astype(np.int64)] = 4
+    blk = Block(max_frames=64, max_payload=400, depth=3, max_lag=2)
+    got_blk, _, _ = blk.run(corpus["iq"], tg, 5000, max_out=64, stride=400)
+    blk.close()
+    print("b200_rx (tagged passes): %d payloads of %d frames" % (len(got_blk), len(rates)))
+    from fun_ofdm_b200.rx import Limits
+    g = C.c_void_p()
+    lim = Limits(64, 400)
+    assert lib.b200rx_group_create((C.c_int * 1)(0), 1, C.byref(lim), C.byref(g)) == 0
+    gp = np.zeros((len(rates), 400), np.uint8)
+    gl = np.zeros(len(rates), np.uint16)
+    gr = np.zeros(len(rates), np.uint8)
+    gs = np.zeros(len(rates), np.uint8)
+    assert lib.b200rx_group_decode_batch(g, iq.ctypes.data, len(iq), lts1.ctypes.data, av.ctypes.data, len(rates), gp.ctypes.data,
+                                         400, gl.ctypes.data, gr.ctypes.data, gs.ctypes.data) == 0
+    lib.b200rx_group_destroy(g)
+    print("group of one device: %d ok" % int((gs == 0).sum()))
     print("sanitize_run: all entry points exercised")
 
 
