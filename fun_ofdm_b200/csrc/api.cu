@@ -550,6 +550,20 @@ int b200rx_device_counters(b200rx_handle *h, void **dev_ptr)
     return B200RX_OK;
 }
 
+int b200rx_copy_counters(b200rx_handle *h, void *dst_dev)
+{
+    if (!h || !dst_dev) return B200RX_E_ARG;
+    CU(h, cudaSetDevice(h->device));
+    if (h->depth > 1 && h->call_idx > 0) {
+        b200rx_handle::Lane &lane = h->lanes[(h->call_idx - 1) % h->depth];
+        CU(h, cudaMemcpyAsync(dst_dev, lane.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, lane.stream));
+        CU(h, cudaEventRecord(lane.done, lane.stream)); // the call is complete, for b200rx_join*, when its counters have been copied
+        return B200RX_OK;
+    }
+    CU(h, cudaMemcpyAsync(dst_dev, h->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+    return B200RX_OK;
+}
+
 uint64_t b200rx_launch_count(const b200rx_handle *h) { return h ? h->launches : 0; }
 uint32_t b200rx_max_steps(const b200rx_handle *h) { return h ? h->max_steps : 0; }
 

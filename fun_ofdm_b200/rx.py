@@ -135,6 +135,8 @@ def load_library():
                                       C.POINTER(C.c_float)]
     L.b200rx_device_counters.restype = C.c_int
     L.b200rx_device_counters.argtypes = [vp, C.POINTER(vp)]
+    L.b200rx_copy_counters.restype = C.c_int
+    L.b200rx_copy_counters.argtypes = [vp, vp]
     L.b200rx_launch_count.restype = u64
     L.b200rx_launch_count.argtypes = [vp]
     L.b200rx_max_steps.restype = u32
@@ -263,6 +265,10 @@ class Receiver:
         st = Stats()
         self._check(self.lib.b200rx_get_stats(self.h, C.byref(st)), "b200rx_get_stats")
         return {k: getattr(st, k) for k, _ in Stats._fields_}
+
+    def copy_counters(self, dst_ptr):
+        """Stream-ordered copy of the most recent call's four counters to device address dst_ptr (b200rx_copy_counters)."""
+        self._check(self.lib.b200rx_copy_counters(self.h, C.c_void_p(dst_ptr)), "b200rx_copy_counters")
 
     def device_counters(self):
         """torch int64[4] view of the handle's device counters {ok, failed, payload bytes, trellis steps}."""

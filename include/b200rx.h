@@ -334,6 +334,10 @@ B200RX_API int b200rx_profile_read(b200rx_handle *h, uint32_t *calls, float *fro
  * {frames ok, frames failed, payload bytes of ok frames, trellis steps}: lets a multi-GPU driver
  * reduce them with one collective (NCCL all-reduce) without a host round trip. */
 B200RX_API int b200rx_device_counters(b200rx_handle *h, void **dev_ptr);
+/* Copies those four counters of the most recent device-buffer call to dst_dev (4 x uint64, device memory) in stream order
+ * right behind that call - before its lane can be given the next batch, which resets them - and inside what b200rx_join*
+ * waits for.  The race-free way to keep per-call counters when calls are pipelined. */
+B200RX_API int b200rx_copy_counters(b200rx_handle *h, void *dst_dev);
 
 /* ---- several GPUs of one box from one process ----
  * Frames are independent (all per-frame state is rebuilt from the frame's own LTS and SIGNAL symbols), so a batch is

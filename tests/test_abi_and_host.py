@@ -59,6 +59,27 @@ def test_no_cpu_fallback(built):
     assert "no CPU path" in str(e.value)
 
 
+def test_group_and_pass_entry_points_fail_loudly_without_a_gpu(built):
+    """The multi-GPU group and the two-phase passes have no CPU path either: creation fails with the device error, and
+    the pass entry points reject a null handle instead of computing anything."""
+    import ctypes as C
+    import torch
+    fo, _ = built
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fun_ofdm_b200.rx import Limits, load_library
+    lib = load_library()
+    g = C.c_void_p()
+    rc = lib.b200rx_group_create((C.c_int * 2)(0, 1), 2, C.byref(Limits(16, 100)), C.byref(g))
+    assert rc != 0 and not g.value
+    assert b"no CPU path" in lib.b200rx_group_last_error(None) or b"no CUDA device" in lib.b200rx_group_last_error(None)
+    assert lib.b200rx_group_create((C.c_int * 2)(0, 0), 2, C.byref(Limits(16, 100)), C.byref(g)) == -1  # a device listed twice
+    for fn in (lib.b200rx_pass_open,):
+        assert fn(None) == -1
+    assert lib.b200rx_pass_put(None, None, 0) == -1 and lib.b200rx_pass_wait(None, 0) == -1
+    assert lib.b200rx_host_is_pinned(None) == 0 and lib.b200rx_sample_bytes(None) == 0
+
+
 def test_product_package_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "fun_ofdm_b200")
     for base, _, files in os.walk(pkg):

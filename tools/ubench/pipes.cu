@@ -21,6 +21,12 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
     asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+__device__ __forceinline__ uint32_t hmin2(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm volatile("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
     uint32_t d;
@@ -63,6 +69,9 @@ __global__ void bench(uint32_t *out, long long *cyc, uint32_t seed, uint32_t neg
             if (MODE == 21) { uint32_t t = __viaddmin_u16x2(q[i], r[i], 0x00FF00FFu); r[i] = __viaddmin_u16x2(r[i], q[i], t); q[i] = imad(q[i], 2u, hset_eq(r[i], t)); } // acs3 register phase
             if (MODE == 22) { uint32_t t = __viaddmin_u16x2(q[i], r[i], 0x00FF00FFu); r[i] = __viaddmin_u16x2(r[i], q[i], t); q[i] = imad(q[i], 2u, r[i] + 0x01000100u - t); } // IADD3 decisions
             if (MODE == 23) r[i] = __vmaxu2(r[i], q[i]) + (r[i] > q[i] ? 1 : 0);                   // VIMNMX + ISETP/SEL
+            if (MODE == 25) r[i] = hmin2(r[i], q[i]);                                             // HMNMX2
+            if (MODE == 26) { r[i] = __viaddmin_u16x2(r[i], q[i], 0x00FF00FFu); q[i] = hmin2(q[i], r[i]); }                            // DPX + HMNMX2
+            if (MODE == 27) { r[i] = imad(r[i], neg1, q[i]); q[i] = hmin2(q[i], r[i]); }                                               // IMAD + HMNMX2
             if (MODE == 24) r[i] = __hmin2(*(__half2*)&r[i], *(__half2*)&q[i]).x > (__half)0 ? r[i] : q[i]; // filler
         }
     }
@@ -136,6 +145,9 @@ int main()
     run<17>("VIADDMNMX + LOP3", 2);
     run<18>("IMAD + LOP3", 2);
     run<19>("VIADDMNMX + 2 IMAD", 3);
+    run<25>("HMNMX2 (min.f16x2)", 1);
+    run<26>("VIADDMNMX + HMNMX2", 2);
+    run<27>("IMAD + HMNMX2", 2);
     run<20>("reg phase: 2 DPX + 2 IMAD", 4);
     run<21>("reg phase: 2 DPX + HSET2 + IMAD", 4);
     run<22>("reg phase: 2 DPX + IADD3 + IMAD", 4);
