@@ -1113,7 +1113,8 @@ namespace {
 // frame list of a scanned capture, written straight into host-mapped memory (one posted PCIe write per frame instead of
 // four device->host copies in front of the synchronisation the caller waits on)
 __global__ void pack_pass_kernel(const SyncSummary *summary, const uint64_t *lts1, const uint32_t *avail, const FrameDesc *desc,
-                                 uint32_t cap, SyncSummary *out_summary, b200rx_pass_frame *out)
+                                 const FrameRot *rot, const double *phase, uint32_t cap, SyncSummary *out_summary,
+                                 b200rx_pass_frame *out)
 {
     const uint32_t n = summary->n_frames < cap ? summary->n_frames : cap;
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1126,6 +1127,8 @@ __global__ void pack_pass_kernel(const SyncSummary *summary, const uint64_t *lts
     o.length = d.length;
     o.rate = d.rate;
     o.status = d.status;
+    o.sts_end = rot ? rot[f].from : 0ull;
+    o.phase = phase ? phase[f] : 0.0;
     out[f] = o;
 }
 
@@ -1311,7 +1314,8 @@ static int pass_scan_impl(b200rx_handle *h, bool tagged, double phase_in, b200rx
     CU(h, launch_frontend(fa, s));
     SyncSummary *out_summary = reinterpret_cast<SyncSummary *>(P.h_list_dev);
     b200rx_pass_frame *out_frames = reinterpret_cast<b200rx_pass_frame *>(P.h_list_dev + sizeof(SyncSummary));
-    pack_pass_kernel<<<(mf + 127) / 128, 128, 0, s>>>(y.summary, y.lts1, y.avail, h->desc, mf, out_summary, out_frames);
+    pack_pass_kernel<<<(mf + 127) / 128, 128, 0, s>>>(y.summary, y.lts1, y.avail, h->desc, tagged ? nullptr : y.rot,
+                                                      tagged ? nullptr : y.phase, mf, out_summary, out_frames);
     CU(h, cudaGetLastError());
     h->launches += 2;
     CU(h, cudaStreamSynchronize(s));

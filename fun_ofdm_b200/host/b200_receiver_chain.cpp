@@ -406,9 +406,12 @@ namespace fun
             if (p < keep_from) keep_from = p;
         }
         if (keep_from < m_base) keep_from = m_base;
-        // m_phase_acc in front of the new buffer: the last synchronised frame's (it either lies in the dropped part,
-        // or it is recomputed from the retained samples and this value is not used)
-        if (keep_from > m_base && res.phase_valid) m_phase = res.last_phase;
+        // m_phase_acc in front of the new buffer: what the last frame whose STS_END tag lies in the dropped part left behind.
+        // (A frame retained for the next call is synchronised again there; the samples in front of its STS_END tag must
+        // then be rotated by its predecessor's phase, timing_sync.cpp:121-125, not by its own.)
+        if (keep_from > m_base)
+            for (uint32_t f = 0; f < nf; f++)
+                if (m_base + frames[f].sts_end < keep_from) m_phase = frames[f].phase;
         const size_t drop = (size_t)(keep_from - m_base);
         size_t kept = 0;
         if (drop < m_buf_n) {

@@ -284,6 +284,8 @@ typedef struct b200rx_pass_frame {
     uint16_t length;  /* LENGTH field (0 when the header failed) */
     uint8_t rate;     /* fun::Rate or B200RX_RATE_INVALID */
     uint8_t status;   /* header verdict, see above */
+    uint64_t sts_end; /* capture index of the STS_END tag that led to this frame (b200rx_pass_scan; 0 for tagged passes) */
+    double phase;     /* m_phase_acc as this frame's synchronisation left it (timing_sync.cpp:114-115; 0 for tagged passes) */
 } b200rx_pass_frame;
 B200RX_API int b200rx_pass_open(b200rx_handle *h);
 B200RX_API int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n_samples);

@@ -193,6 +193,8 @@ int b200rx_pass_scan_tagged(b200rx_handle *h, b200rx_pass_frame *frames, uint32_
             frames[nf].length = h->pass_len[nf];
             frames[nf].rate = rate;
             frames[nf].status = h->pass_status[nf] == B200RX_ST_CRC_FAIL ? (uint8_t)B200RX_ST_OK : h->pass_status[nf];
+            frames[nf].sts_end = 0;
+            frames[nf].phase = 0.0;
         }
     }
     h->pass_frames = nf;
@@ -221,6 +223,8 @@ int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frame
         frames[f].rate = rate[f];
         const uint8_t st = h->pass_status[f];
         frames[f].status = (st == B200RX_ST_CRC_FAIL) ? (uint8_t)B200RX_ST_OK : st; // the header verdict only
+        frames[f].sts_end = 0;  // the double carries no phase state: its reference blocks synchronise every capture afresh
+        frames[f].phase = 0.0;
     }
     return B200RX_OK;
 }
