@@ -156,7 +156,10 @@ namespace fun
             return;
         }
         m_select.resize(m_max_frames);
-        set_copy_threads(4);
+        {   // staging threads for long calls: half the cores, 2 .. 8
+            unsigned hw = std::thread::hardware_concurrency() / 2;
+            set_copy_threads(hw < 2 ? 2 : (hw > 8 ? 8 : hw));
+        }
     }
 
     b200_receiver_chain::~b200_receiver_chain()
