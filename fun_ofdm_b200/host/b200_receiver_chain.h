@@ -68,7 +68,7 @@ namespace fun
         static void free_samples(std::complex<double> *p);
 
         void set_max_lag(unsigned calls) { m_max_lag = calls; }
-        void set_copy_threads(unsigned n); // host threads used to stage calls of >= 64 Ki samples (default: half the cores, 2 .. 8; 1 = caller's thread only)
+        void set_copy_threads(unsigned n); // host threads used to stage calls of >= 64 Ki samples (default 4; 1 = caller's thread only)
 
         struct counters_t { uint64_t samples, calls, frames_found, frames_ok, frames_crc_fail, headers_bad, frames_truncated; };
         counters_t counters() const { return m_counters; }

@@ -353,3 +353,33 @@ def test_full_size_fixture_frames(rx_factory):
         assert np.array_equal(got, want), (k, row)
         if crc_ok:
             assert (bytes(pl[k, :dlen]) == payload.tobytes()) == bool(pl_equal), (k, row)
+
+
+def test_copy_counters_is_ordered_behind_its_own_call(ref, rx_factory):
+    """b200rx_copy_counters: with calls pipelined over lanes every call's four counters land where they were asked for,
+    although the lane's next batch resets the live counters (the race a copy on another stream would lose)."""
+    rng = np.random.default_rng(21)
+    rx = rx_factory(64, 600)
+    corpora = [make_corpus(ref, rng, [10, 3, 0, 8][: 2 + k % 3], [500, 77, 10, 300][: 2 + k % 3], snr_db=28) for k in range(7)]
+    dev = torch.device("cuda:0")
+    rx.set_pipeline_depth(3)
+    rows = torch.zeros((len(corpora), 4), dtype=torch.int64, device=dev)
+    keep = []
+    for k, c in enumerate(corpora):
+        n = len(c["lts1"])
+        t = [torch.from_numpy(c["iq"].view(np.float64)).to(dev), torch.from_numpy(c["lts1"]).to(dev), torch.from_numpy(c["avail"]).to(dev),
+             torch.zeros((n, 600), dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.int16, device=dev),
+             torch.zeros(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)]
+        keep.append(t)
+        torch.cuda.synchronize()
+        rx.decode_batch_dev(*t)
+        rx.copy_counters(rows[k].data_ptr())
+    rx.join(0)
+    rx.synchronize()
+    rx.set_pipeline_depth(1)
+    got = rows.cpu().numpy()
+    for k, c in enumerate(corpora):
+        st = keep[k][6].cpu().numpy()
+        ln = keep[k][4].cpu().numpy().astype(np.uint16).astype(np.int64)
+        assert got[k, 0] == int((st == 0).sum()) and got[k, 0] + got[k, 1] == len(st), (k, got[k], st)
+        assert got[k, 2] == int(ln[st == 0].sum()), (k, got[k])
