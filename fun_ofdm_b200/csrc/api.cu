@@ -1376,6 +1376,7 @@ int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload
     // however few frames there are, generation 3 is built for a full GPU
     Tuning tn = h->tn;
     if (tn.acs_gen == 3 && n_sel <= 2048) tn.acs_gen = 2;
+    if (tn.acs_gen == 2 && tn.acs_lb == 0 && n_sel <= 64) tn.acs_lb = 5; // a warp per frame: 0.65 instead of 0.68 ms for 12 096 steps
     const b200rx_handle::SyncScratch &y = h->sy[li];
     const OutPtrs o{payload_out ? P.d_payload : nullptr, payload_stride, nullptr, nullptr, P.d_status};
     int rc = launch_range(h, tn, s, lo, hi - lo, P.d_iq, P.fill, y.lts1, y.avail, o, nullptr, nullptr, P.tagged ? nullptr : y.rot,
