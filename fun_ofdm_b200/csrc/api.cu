@@ -102,6 +102,10 @@ struct b200rx_handle {
         uint8_t *d_status = nullptr, *d_select = nullptr;      // [max_frames]
         uint8_t *h_list = nullptr, *h_list_dev = nullptr;      // pinned + mapped: SyncSummary, then b200rx_pass_frame[max_frames]
         uint8_t *h_select = nullptr;                           // pinned [max_frames]
+        // the scan phase as a CUDA graph (captured once per lane; re-captured when the staging moves or grows)
+        cudaGraphExec_t scan_exec = nullptr;
+        ScanParams *h_sp = nullptr, *d_sp = nullptr;           // pinned / device parameter block
+        const uint8_t *scan_iq = nullptr; uint64_t scan_cap = 0; int scan_fmt = -1; double scan_scale = 0.0;
         uint64_t fill = 0;                                     // samples staged so far
         uint32_t n_frames = 0;
         bool scanned = false, busy = false, tagged = false;
@@ -380,6 +384,9 @@ int b200rx_destroy(b200rx_handle *h)
         cudaFree(P.d_iq); cudaFree(P.d_payload); cudaFree(P.d_status); cudaFree(P.d_select);
         if (P.h_list) cudaFreeHost(P.h_list);
         if (P.h_select) cudaFreeHost(P.h_select);
+        if (P.scan_exec) cudaGraphExecDestroy(P.scan_exec);
+        if (P.h_sp) cudaFreeHost(P.h_sp);
+        cudaFree(P.d_sp);
     }
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->ring) if (e) cudaEventDestroy(e);
@@ -426,6 +433,7 @@ int b200rx_set_tuning(b200rx_handle *h, const char *key, int64_t value)
     else if (!strcmp(key, "h2d_chunk_min")) field = &h->tn.h2d_chunk_min;
     else if (!strcmp(key, "pull_mode")) field = &h->tn.pull_mode;
     else if (!strcmp(key, "fe_split")) field = &h->tn.fe_split;
+    else if (!strcmp(key, "scan_graph")) field = &h->tn.scan_graph;
     else return fail(h, B200RX_E_ARG, "b200rx_set_tuning: unknown key");
     int rc = b200rx_synchronize(h); // nothing in flight may see two settings
     if (rc != B200RX_OK) return rc;
@@ -957,7 +965,12 @@ int launch_sync_lane(b200rx_handle *h, cudaStream_t s, int lane, const void *iq_
     a.tags = tags_dev;
     a.ev_x = y.ev_x; a.ev_count = y.ev_count; a.ev_cap = h->sy_ev_cap;
     a.rec = y.rec; a.cta_ev = y.cta_ev; a.cta_cnt = y.cta_cnt;
-    if (!h->origins.empty()) { // consumed by this call
+    if (!h->origins.empty() && h->origins.size() <= 16) { // consumed by this call; a short list rides in the kernel arguments
+        a.n_inline = (uint32_t)h->origins.size();
+        for (uint32_t o = 0; o < a.n_inline; o++) a.origins_inline[o] = h->origins[o];
+        h->origins.clear();
+    }
+    if (!h->origins.empty()) {
         const uint32_t no = (uint32_t)h->origins.size();
         if (no > h->d_origins_cap[lane]) {
             if (h->d_origins[lane]) { CU(h, cudaStreamSynchronize(s)); cudaFree(h->d_origins[lane]); h->d_origins[lane] = nullptr; }
@@ -1266,6 +1279,83 @@ int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n_samples)
     return B200RX_OK;
 }
 
+namespace {
+
+// Captures the launches of one scan (parameter copy, detector, event scan, LTS synchronisation, frame list, SIGNAL decode,
+// frame-list export) on the lane's stream into a graph whose kernels take this call's scalars from the lane's ScanParams
+// block.  A streaming caller scans every 4096 samples: replaying one graph costs one driver call instead of eight.
+int build_scan_graph(b200rx_handle *h, int li)
+{
+    b200rx_handle::PassLane &P = h->pl[li];
+    const size_t bps = sample_bytes(h->fmt);
+    const uint64_t cap = P.d_iq_cap / bps;
+    if (P.scan_exec) { cudaGraphExecDestroy(P.scan_exec); P.scan_exec = nullptr; }
+    if (cap == 0) return B200RX_E_ARG;
+    int rc = ensure_sync_scratch(h, li);
+    if (rc != B200RX_OK) return rc;
+    cudaStream_t s = P.stream;
+    b200rx_handle::SyncScratch &y = h->sy[li];
+    const uint32_t n_ctas = sync_cta_count(cap);
+    if (n_ctas > y.cta_cap) {
+        CU(h, cudaStreamSynchronize(s));
+        cudaFree(y.cta_ev); cudaFree(y.cta_cnt);
+        y.cta_ev = nullptr; y.cta_cnt = nullptr; y.cta_cap = 0;
+        cudaError_t e = cudaMalloc((void **)&y.cta_ev, (size_t)n_ctas * sizeof(CtaEvents));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&y.cta_cnt, n_ctas);
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "sync scratch (detector event lists)", e);
+        y.cta_cap = n_ctas;
+    }
+    if (!P.h_sp) {
+        cudaError_t e = cudaHostAlloc((void **)&P.h_sp, sizeof(ScanParams), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&P.d_sp, sizeof(ScanParams));
+        if (e != cudaSuccess) return fail(h, B200RX_E_NOMEM, "scan parameter block", e);
+        memset(P.h_sp, 0, sizeof(ScanParams));
+    }
+    use_lane(h, li);
+    const uint32_t mf = h->limits.max_frames;
+    SyncArgs a{};
+    a.iq = P.d_iq; a.fmt = h->fmt; a.scale = h->scale; a.n_samples = cap; a.grid_samples = cap; a.sp = P.d_sp;
+    a.rot_in = make_double2(1.0, 0.0);
+    a.max_frames = mf; a.tags = nullptr;
+    a.ev_x = y.ev_x; a.ev_count = y.ev_count; a.ev_cap = h->sy_ev_cap;
+    a.rec = y.rec; a.cta_ev = y.cta_ev; a.cta_cnt = y.cta_cnt;
+    a.lts1 = y.lts1; a.avail = y.avail; a.rot = y.rot; a.phase = y.phase; a.summary = y.summary;
+    FrontendArgs fa{};
+    fa.iq = P.d_iq; fa.fmt = h->fmt; fa.scale = h->scale; fa.iq_samples = cap; fa.sp = P.d_sp;
+    fa.lts1 = y.lts1; fa.avail = y.avail;
+    fa.n_frames = (uint32_t)((cap / 17 + 2 < (uint64_t)mf) ? cap / 17 + 2 : mf);
+    fa.desc = h->desc; fa.bm = h->bm; fa.bm_stride = h->max_steps; fa.max_steps = h->max_steps;
+    fa.max_len = h->limits.max_payload_bytes; fa.header_only = 2; fa.hinv_out = h->hinv; fa.rot = y.rot;
+    fa.n_live = &y.summary->n_frames;
+    SyncSummary *out_summary = reinterpret_cast<SyncSummary *>(P.h_list_dev);
+    b200rx_pass_frame *out_frames = reinterpret_cast<b200rx_pass_frame *>(P.h_list_dev + sizeof(SyncSummary));
+
+    CU(h, cudaStreamSynchronize(s));
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return fail(h, B200RX_E_CUDA, "scan graph: begin capture", e);
+    e = cudaMemcpyAsync(P.d_sp, P.h_sp, sizeof(ScanParams), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_sync(a, s);
+    if (e == cudaSuccess) e = launch_frontend(fa, s);
+    if (e == cudaSuccess) {
+        pack_pass_kernel<<<(mf + 127) / 128, 128, 0, s>>>(y.summary, y.lts1, y.avail, h->desc, y.rot, y.phase, mf, out_summary, out_frames);
+        e = cudaGetLastError();
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(s, &graph);
+    if (e == cudaSuccess) e = e_end;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&P.scan_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        P.scan_exec = nullptr;
+        (void)cudaGetLastError();
+        return fail(h, B200RX_E_CUDA, "scan graph: capture", e);
+    }
+    P.scan_iq = P.d_iq; P.scan_cap = cap; P.scan_fmt = h->fmt; P.scan_scale = h->scale;
+    return B200RX_OK;
+}
+
+} // namespace
+
 static int pass_scan_impl(b200rx_handle *h, bool tagged, double phase_in, b200rx_pass_frame *frames, uint32_t frames_cap,
                           b200rx_sync_result *res)
 {
@@ -1301,6 +1391,29 @@ static int pass_scan_impl(b200rx_handle *h, bool tagged, double phase_in, b200rx
         tag_frames_kernel<<<1, 1024, 0, s>>>(t.ev_x, t.ev_count, h->sy_ev_cap, mf, P.fill, t.lts1, t.avail, t.summary);
         CU(h, cudaGetLastError());
         h->launches += 2;
+    } else if (h->tn.scan_graph && h->origins.size() <= 16) {
+        // the whole scan as one graph launch (see build_scan_graph)
+        if (!P.scan_exec || P.scan_iq != P.d_iq || P.scan_cap != P.d_iq_cap / sample_bytes(h->fmt) || P.scan_fmt != h->fmt ||
+            P.scan_scale != h->scale) {
+            rc = build_scan_graph(h, li);
+            if (rc != B200RX_OK) return rc;
+        }
+        ScanParams &sp = *P.h_sp;
+        sp.n_samples = P.fill;
+        sp.x_limit = P.fill > 160 ? P.fill - 160 : 0; // timing_sync.cpp:68: x < input.size() - CARRYOVER_LENGTH
+        sp.rot_in = make_double2(cos(phase_in), sin(phase_in)); // timing_sync.cpp:124
+        sp.n_origins = (uint32_t)h->origins.size();
+        for (uint32_t o = 0; o < sp.n_origins; o++) sp.origins[o] = h->origins[o];
+        h->origins.clear();
+        CU(h, cudaGraphLaunch(P.scan_exec, s));
+        h->launches += 7;
+        CU(h, cudaStreamSynchronize(s));
+        *res = *reinterpret_cast<const SyncSummary *>(P.h_list);
+        if (!res->phase_valid) res->last_phase = phase_in;
+        P.n_frames = res->n_frames < mf ? res->n_frames : mf;
+        const uint32_t n_copy = P.n_frames < frames_cap ? P.n_frames : frames_cap;
+        if (n_copy) memcpy(frames, P.h_list + sizeof(SyncSummary), (size_t)n_copy * sizeof(b200rx_pass_frame));
+        return B200RX_OK;
     } else {
         rc = launch_sync_lane(h, s, li, P.d_iq, P.fill, phase_in, nullptr);
         if (rc != B200RX_OK) return rc;
@@ -1308,7 +1421,9 @@ static int pass_scan_impl(b200rx_handle *h, bool tagged, double phase_in, b200rx
     const b200rx_handle::SyncScratch &y = h->sy[li];
     FrontendArgs fa{}; // SIGNAL decode of every frame found: descriptor with the full status logic
     fa.iq = P.d_iq; fa.fmt = h->fmt; fa.scale = h->scale; fa.iq_samples = P.fill;
-    fa.lts1 = y.lts1; fa.avail = y.avail; fa.n_frames = mf; fa.desc = h->desc; fa.bm = h->bm;
+    // frames start at distinct STS_END / LTS1 tags, at least 17 samples apart: the grid need not cover more slots than that
+    const uint32_t slots = (uint32_t)((P.fill / 17 + 2 < (uint64_t)mf) ? P.fill / 17 + 2 : mf);
+    fa.lts1 = y.lts1; fa.avail = y.avail; fa.n_frames = tagged ? mf : slots; fa.desc = h->desc; fa.bm = h->bm;
     fa.bm_stride = h->max_steps; fa.max_steps = h->max_steps; fa.max_len = h->limits.max_payload_bytes;
     fa.header_only = 2; fa.hinv_out = h->hinv; fa.rot = tagged ? nullptr : y.rot; fa.n_live = &y.summary->n_frames;
     CU(h, launch_frontend(fa, s));

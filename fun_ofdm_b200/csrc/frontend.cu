@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(FE_WARPS * 32, 40 / FE_WARPS) frontend_kernel(
     }
     const uint64_t p = a.lts1[frame];
     uint32_t avail = a.avail[frame];
-    if (p >= a.iq_samples) avail = 0;
-    else if ((uint64_t)avail > a.iq_samples - p) avail = (uint32_t)(a.iq_samples - p);
+    const uint64_t iq_samples = a.sp ? a.sp->n_samples : a.iq_samples;
+    if (p >= iq_samples) avail = 0;
+    else if ((uint64_t)avail > iq_samples - p) avail = (uint32_t)(iq_samples - p);
     const Window win{a.iq, p, a.scale};
     RotCtx rc{};
     if constexpr (ROT) {

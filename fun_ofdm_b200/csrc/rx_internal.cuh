@@ -167,6 +167,18 @@ struct CtaEvents {    // STS_END tags one detector CTA found, in stream order (o
 
 typedef b200rx_sync_result SyncSummary;
 
+// Per-call scalars of a scan (b200rx_pass_scan) when its launches are replayed as a CUDA graph: the captured kernels have
+// fixed arguments and read what changes from call to call here (device memory, refreshed by a copy node at the head of the
+// graph from the pinned block the host fills in).
+struct ScanParams {
+    uint64_t n_samples;     // samples staged for this pass
+    uint64_t x_limit;       // STS_END tags at or beyond it wait for the next capture (timing_sync.cpp:68)
+    double2 rot_in;         // (cos, sin) of m_phase_acc in front of the capture
+    int64_t origins[16];    // work() buffer origins (b200rx_set_receive_origins), ascending
+    uint32_t n_origins;
+    uint32_t pad;
+};
+
 struct SyncArgs {
     const void *iq;       // samples in format `fmt`
     int fmt;
@@ -182,6 +194,10 @@ struct SyncArgs {
     uint32_t ev_cap;
     const int64_t *origins; // device, ascending: work() buffer origins of a chunked stream (null: one buffer at -160)
     uint32_t n_origins;
+    const ScanParams *sp;   // non-null (device): n_samples, rot_in and the origins come from there, grids cover grid_samples
+    uint64_t grid_samples;
+    int64_t origins_inline[16]; // the same list when it has at most 16 entries: travels in the kernel arguments (origins
+    uint32_t n_inline;          // is then null) - a streaming call per 4096 samples has no copy to spare
     SyncRec *rec;         // scratch [ev_cap]
     uint64_t *lts1;       // [max_frames]
     uint32_t *avail;      // [max_frames]
@@ -206,6 +222,7 @@ struct Tuning {
     int pull_mode = -1;     // host-buffer ingest: 0 DMA copy, 1 GPU pull when the buffer is pinned, 2 alternate, -1 by format
     int inflight = 1;       // batches the caller keeps in flight on this handle (pipeline depth): the ACS launcher sizes its
                             // warps for the GPU being shared, not for one batch alone
+    int scan_graph = 1;     // b200rx_pass_scan: replay the scan launches as a CUDA graph (1) or issue them one by one (0)
     int fe_split = 1;       // front end: 1 = header kernel + one warp per OFDM symbol over all frames, 0 = one CTA per frame
 };
 
@@ -230,6 +247,7 @@ struct FrontendArgs {
     const FrameRot *rot;     // per frame, or null: samples are used as they are
     const uint32_t *n_live;  // device count of valid frames (slots beyond it become B200RX_ST_NO_FRAME), or null
     int sm_count;            // multiprocessors of the device (persistent grids); 0 = 148
+    const ScanParams *sp;    // non-null (device): iq_samples comes from there (graph-replayed scan)
     const uint8_t *select;   // per frame, or null: frames with select[f] == 0 are skipped (B200RX_ST_NO_FRAME; b200rx_pass_decode)
     // taps (may be null)
     double2 *dbg_eq;

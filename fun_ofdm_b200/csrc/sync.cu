@@ -68,8 +68,14 @@ __device__ __forceinline__ void window16(const double *src, double (&w)[DET_PER_
 // frame_detector::work (frame_detector.cpp:41-92).  Per CTA DT tags; per thread 8 plateau flags.
 template <int FMT>
 __global__ void __launch_bounds__(DET_THREADS) detect_kernel(const void *iq, double scale, uint64_t n, uint8_t *tags,
-                                                             CtaEvents *cta_ev, uint8_t *cta_cnt, uint64_t x_limit)
+                                                             CtaEvents *cta_ev, uint8_t *cta_cnt, uint64_t x_limit,
+                                                             const ScanParams *sp)
 {
+    if (sp) { // graph replay: the grid covers the lane's capacity, the capture ends where this call's samples end
+        n = sp->n_samples;
+        x_limit = sp->x_limit;
+        if ((uint64_t)blockIdx.x * DT >= n) return;
+    }
     __shared__ double s_re[DET_SAMPLES], s_im[DET_SAMPLES];
     __shared__ uint32_t s_nev;
     __shared__ uint16_t s_ev[CtaEvents::CAP];
@@ -169,8 +175,10 @@ __global__ void __launch_bounds__(DET_THREADS) detect_kernel(const void *iq, dou
 constexpr int SCAN_THREADS = 1024;
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_events_kernel(const CtaEvents *cta_ev, const uint8_t *cta_cnt, uint32_t n_ctas,
-                                                                   uint64_t *ev_x, uint32_t *ev_count, uint32_t ev_cap)
+                                                                   uint64_t *ev_x, uint32_t *ev_count, uint32_t ev_cap,
+                                                                   const ScanParams *sp)
 {
+    if (sp) n_ctas = (uint32_t)((sp->n_samples + DT - 1) / DT);
     __shared__ uint32_t s_warp[32], s_lost[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t per = (n_ctas + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -217,13 +225,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_events_kernel(const CtaEven
     }
 }
 
+struct OriginList { int64_t v[16]; uint32_t n; };
+
 // One CTA per STS_END event: 96 candidate offsets, 64 taps each (timing_sync.cpp:74-87), then the peak logic
 // (timing_sync.cpp:89-118) on one thread.
 template <int FMT>
 __global__ void __launch_bounds__(128) lts_sync_kernel(const void *iq, double scale, uint64_t n, const uint64_t *ev_x,
                                                        const uint32_t *ev_count, uint32_t ev_cap, SyncRec *rec,
-                                                       const int64_t *origins, uint32_t n_origins)
+                                                       const int64_t *origins, uint32_t n_origins, const OriginList inl,
+                                                       const ScanParams *sp)
 {
+    if (sp) n = sp->n_samples;
     __shared__ double2 s_s[160];
     __shared__ double s_val[96];
     const int tid = threadIdx.x;
@@ -285,6 +297,15 @@ __global__ void __launch_bounds__(128) lts_sync_kernel(const void *iq, double sc
                         const int64_t v = origins[o];
                         if (v <= (int64_t)x) origin = v; else break;
                     }
+                    for (uint32_t o = 0; o < inl.n; o++) { // the short list of a streaming call (kernel arguments)
+                        const int64_t v = inl.v[o];
+                        if (v <= (int64_t)x) origin = v; else break;
+                    }
+                    if (sp)
+                        for (uint32_t o = 0; o < sp->n_origins; o++) { // ... or of a graph-replayed one (parameter block)
+                            const int64_t v = sp->origins[o];
+                            if (v <= (int64_t)x) origin = v; else break;
+                        }
                     if ((int64_t)x + lts_offset >= origin) {
                         r.found = 1;
                         r.lts1 = (int64_t)x + lts_offset + 24;
@@ -310,8 +331,10 @@ constexpr int BF_THREADS = 1024;
 __global__ void __launch_bounds__(BF_THREADS) build_frames_kernel(const SyncRec *rec, const uint32_t *ev_count, uint32_t ev_cap,
                                                                   uint64_t n, double2 rot_in, uint32_t max_frames,
                                                                   uint64_t *lts1, uint32_t *avail, FrameRot *rot,
-                                                                  double *phase, uint8_t *tags, SyncSummary *summary)
+                                                                  double *phase, uint8_t *tags, SyncSummary *summary,
+                                                                  const ScanParams *sp)
 {
+    if (sp) { n = sp->n_samples; rot_in = sp->rot_in; }
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -432,32 +455,39 @@ cudaError_t launch_sync(const SyncArgs &a, cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(a.ev_count, 0, 2 * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
-    if (a.n_samples > 0) {
-        const unsigned blocks = sync_cta_count(a.n_samples);
+    const uint64_t grid_n = a.sp ? a.grid_samples : a.n_samples; // graph replay: launch for the lane's capacity
+    if (grid_n > 0) {
+        const unsigned blocks = sync_cta_count(grid_n);
         const uint64_t x_limit = a.n_samples > 160 ? a.n_samples - 160 : 0; // timing_sync.cpp:68: x < input.size() - CARRYOVER_LENGTH
         switch (a.fmt) {
-            case FMT_FC64: detect_kernel<FMT_FC64><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit); break;
-            case FMT_FC32: detect_kernel<FMT_FC32><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit); break;
-            case FMT_SC16: detect_kernel<FMT_SC16><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit); break;
+            case FMT_FC64: detect_kernel<FMT_FC64><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit, a.sp); break;
+            case FMT_FC32: detect_kernel<FMT_FC32><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit, a.sp); break;
+            case FMT_SC16: detect_kernel<FMT_SC16><<<blocks, DET_THREADS, 0, s>>>(a.iq, a.scale, a.n_samples, a.tags, a.cta_ev, a.cta_cnt, x_limit, a.sp); break;
             default: return cudaErrorInvalidValue;
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        scan_events_kernel<<<1, SCAN_THREADS, 0, s>>>(a.cta_ev, a.cta_cnt, blocks, a.ev_x, a.ev_count, a.ev_cap);
+        scan_events_kernel<<<1, SCAN_THREADS, 0, s>>>(a.cta_ev, a.cta_cnt, blocks, a.ev_x, a.ev_count, a.ev_cap, a.sp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         // enough CTAs for one event each at the usual rates; the kernel strides over the rest
-        const unsigned lts_grid = a.ev_cap < 4096u ? a.ev_cap : 4096u;
+        // (an STS_END tag needs 17 samples of its own: a capture of n samples holds at most n / 17 events)
+        unsigned lts_grid = a.ev_cap < 4096u ? a.ev_cap : 4096u;
+        const uint64_t ev_bound = grid_n / 17 + 1;
+        if (ev_bound < lts_grid) lts_grid = (unsigned)ev_bound;
+        OriginList inl;
+        inl.n = a.n_inline <= 16 ? a.n_inline : 0;
+        for (uint32_t o = 0; o < 16; o++) inl.v[o] = o < inl.n ? a.origins_inline[o] : 0;
         switch (a.fmt) {
-            case FMT_FC64: lts_sync_kernel<FMT_FC64><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins); break;
-            case FMT_FC32: lts_sync_kernel<FMT_FC32><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins); break;
-            default: lts_sync_kernel<FMT_SC16><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins); break;
+            case FMT_FC64: lts_sync_kernel<FMT_FC64><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins, inl, a.sp); break;
+            case FMT_FC32: lts_sync_kernel<FMT_FC32><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins, inl, a.sp); break;
+            default: lts_sync_kernel<FMT_SC16><<<lts_grid, 128, 0, s>>>(a.iq, a.scale, a.n_samples, a.ev_x, a.ev_count, a.ev_cap, a.rec, a.origins, a.n_origins, inl, a.sp); break;
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     build_frames_kernel<<<1, BF_THREADS, 0, s>>>(a.rec, a.ev_count, a.ev_cap, a.n_samples, a.rot_in, a.max_frames,
-                                                 a.lts1, a.avail, a.rot, a.phase, a.tags, a.summary);
+                                                 a.lts1, a.avail, a.rot, a.phase, a.tags, a.summary, a.sp);
     return cudaGetLastError();
 }
 

@@ -172,6 +172,14 @@ namespace fun
         delete m_pool;
     }
 
+    int b200_receiver_chain::set_tuning(const char *key, long long value)
+    {
+        if (!m_handle) return B200RX_E_DEVICE;
+        std::vector<std::vector<unsigned char> > sink;
+        collect(sink, true); // nothing in flight may see two settings (payloads collected here are dropped: call it between streams)
+        return b200rx_set_tuning(m_handle, key, (int64_t)value);
+    }
+
     void b200_receiver_chain::set_copy_threads(unsigned n)
     {
         if (n < 1) n = 1;

@@ -68,6 +68,7 @@ namespace fun
         static void free_samples(std::complex<double> *p);
 
         void set_max_lag(unsigned calls) { m_max_lag = calls; }
+        int set_tuning(const char *key, long long value); // b200rx_set_tuning on the chain's handle (never changes results)
         void set_copy_threads(unsigned n); // host threads used to stage calls of >= 64 Ki samples (default 4; 1 = caller's thread only)
 
         struct counters_t { uint64_t samples, calls, frames_found, frames_ok, frames_crc_fail, headers_bad, frames_truncated; };

@@ -118,6 +118,11 @@ API void *b200host_chain_new2(int device, unsigned max_frames, unsigned max_payl
     return c;
 }
 
+API int b200host_chain_set_tuning(void *chain, const char *key, long long value)
+{
+    return static_cast<fun::b200_receiver_chain *>(chain)->set_tuning(key, value);
+}
+
 API void b200host_chain_set_copy_threads(void *chain, unsigned n) { static_cast<fun::b200_receiver_chain *>(chain)->set_copy_threads(n); }
 
 API double *b200host_alloc_samples(long n) { return reinterpret_cast<double *>(fun::b200_receiver_chain::alloc_samples((size_t)n)); }

@@ -150,6 +150,7 @@ int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n, double, uint8_t
 
 // ---- two-phase passes: scan = the same capture logic, decode = hand out what the scan already computed ----
 int b200rx_set_pipeline_depth(b200rx_handle *, uint32_t) { return B200RX_OK; }
+int b200rx_set_tuning(b200rx_handle *, const char *, int64_t) { return B200RX_OK; }
 int b200rx_host_is_pinned(const void *) { return 0; }
 int b200rx_set_sample_format(b200rx_handle *h, int fmt, double) { h->fmt = fmt; return B200RX_OK; }
 int b200rx_pass_open(b200rx_handle *h) { h->pass_iq.clear(); h->pass_raw.clear(); h->pass_frames = 0; return B200RX_OK; }

@@ -39,11 +39,13 @@ def main():
     warm = Chain(max_frames=2048, max_payload=1500)  # CUDA context, module load
     warm.run(np.tile(frame, 4), 4096)
     warm.close()
-    for n_frames, chunk in ((100, 4096), (2000, 4096), (8000, 65536), (8000, 1 << 20)):
-        x = np.concatenate([np.tile(frame, n_frames), np.zeros(10 * len(frame), complex)])
+    # (frames, zero pad in frame lengths, samples per call); the first row is examples/test_sim.cpp as it is: 100 frames
+    # followed by 1000 frame lengths of zeros (test_sim.cpp:58-71), 4096-sample calls
+    for n_frames, pad, chunk in ((100, 1000, 4096), (100, 10, 4096), (2000, 10, 4096), (8000, 10, 65536), (8000, 10, 1 << 20)):
+        x = np.concatenate([np.tile(frame, n_frames), np.zeros(pad * len(frame), complex)])
         chain = ref.chain_new()
         want, t_ref = ref.chain_run(chain, x, chunk, drain=8, max_len=1500)  # native loop; the drain is not timed
-        point = {"frames": n_frames, "chunk_samples": chunk, "samples": int(len(x)),
+        point = {"frames": n_frames, "zero_pad_frame_lengths": pad, "chunk_samples": chunk, "samples": int(len(x)),
                  "reference_chain": {"payloads": len(want), "seconds": t_ref, "mbit_s": len(want) * bits / t_ref / 1e6,
                                      "msamples_s": len(x) / t_ref / 1e6}, "b200_receiver_chain": {}}
         # variants of the same feed loop (native, host_capi.cpp b200host_chain_run; seconds include the final flush):
