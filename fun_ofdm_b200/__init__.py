@@ -9,7 +9,7 @@ streams and ``torch.distributed`` only.  There is no CPU implementation of the p
 from .rx import (  # noqa: F401
     B200RxError,
     Receiver,
-    FMT_FC64, FMT_FC32, FMT_SC16,
+    FMT_FC64, FMT_FC32, FMT_SC16, FMT_TAGGED_FC64,
     ST_OK, ST_HDR_PARITY, ST_HDR_RATE, ST_CRC_FAIL, ST_TRUNCATED, ST_TOO_LONG,
     RATE_PARAMS, lib_path, load_library, num_symbols, window_samples,
 )

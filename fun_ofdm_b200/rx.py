@@ -8,8 +8,9 @@ ST_OK, ST_HDR_PARITY, ST_HDR_RATE, ST_CRC_FAIL, ST_TRUNCATED, ST_TOO_LONG = rang
 ST_NO_FRAME = 255
 RATE_INVALID = 255
 FMT_FC64, FMT_FC32, FMT_SC16 = 0, 1, 2
+FMT_TAGGED_FC64 = 3  # fun::tagged_sample structs, 24 bytes each (b200rx_pass_scan_tagged, decode entry points)
 MAX_INFLIGHT = 3  # B200RX_MAX_INFLIGHT
-_FMT_BYTES = {FMT_FC64: 16, FMT_FC32: 8, FMT_SC16: 4}
+_FMT_BYTES = {FMT_FC64: 16, FMT_FC32: 8, FMT_SC16: 4, FMT_TAGGED_FC64: 24}
 
 # fun::Rate -> (rate_field, cbps, dbps, bpsc)   reference src/rates.h:52-196
 RATE_PARAMS = {

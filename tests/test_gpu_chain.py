@@ -287,3 +287,48 @@ def test_scan_as_graph_and_launch_by_launch_agree(ref):
             outs.append(got)
         assert outs[0] == outs[1] == want, (chunk, len(outs[0]), len(outs[1]), len(want))
         assert len(want) >= 20
+
+
+def test_pass_api_rejects_misuse_and_releases_memory(ref):
+    """Order and format errors of the two-phase pass entry points come back as B200RX_E_ARG (never a crash, never a
+    silent fallback), and handles / chains give their device memory back."""
+    import torch
+    import fun_ofdm_b200 as fo
+    from fun_ofdm_b200.rx import SyncResult
+    E_ARG = -1
+    rx = fo.Receiver(0, 32, 600)
+    L, h = rx.lib, rx.h
+    frames = (C.c_uint8 * (32 * 32))()
+    res = SyncResult()
+    x = np.zeros(1000, np.complex128)
+    assert L.b200rx_pass_put(h, x.ctypes.data, 1000) == E_ARG                        # no pass open
+    assert L.b200rx_pass_scan(h, 0.0, frames, 32, C.byref(res)) == E_ARG
+    assert L.b200rx_pass_open(h) == 0
+    t = C.c_uint64()
+    sel = (C.c_uint8 * 32)()
+    st = (C.c_uint8 * 32)()
+    assert L.b200rx_pass_decode(h, sel, None, 600, st, C.byref(t)) == E_ARG           # not scanned yet
+    assert L.b200rx_pass_put(h, x.ctypes.data, 1000) == 0
+    assert L.b200rx_pass_scan_tagged(h, frames, 32, C.byref(res)) == E_ARG            # fc64 samples are not tagged structs
+    assert L.b200rx_pass_scan(h, 0.0, frames, 32, C.byref(res)) == 0 and res.n_frames == 0
+    assert L.b200rx_pass_scan(h, 0.0, frames, 32, C.byref(res)) == E_ARG              # scanned already
+    assert L.b200rx_pass_put(h, x.ctypes.data, 1000) == E_ARG
+    assert L.b200rx_pass_decode(h, sel, None, 600, st, C.byref(t)) == 0 and t.value == 0  # nothing selected: no ticket
+    assert L.b200rx_pass_poll(h, 0) == 1 and L.b200rx_pass_wait(h, 0) == 0
+    assert L.b200rx_set_sample_format(h, fo.FMT_TAGGED_FC64, 1.0) == 0
+    assert L.b200rx_pass_open(h) == 0
+    assert L.b200rx_pass_scan(h, 0.0, frames, 32, C.byref(res)) == E_ARG              # tagged streams are not raw captures
+    pl = np.zeros((32, 600), np.uint8)
+    got = L.b200rx_receive(h, x.ctypes.data, 1000, 0.0, pl.ctypes.data, 600, None, None, st, None, C.byref(res))
+    assert got == E_ARG and b"tagged" in L.b200rx_last_error(h)
+    rx.close()
+
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(6):
+        ch = Chain(max_frames=64, max_payload=600, depth=4, max_lag=3)
+        ch.run(np.zeros(20000, complex), 4096)
+        ch.close()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, (free0, free1)   # nothing but allocator slack stays behind
