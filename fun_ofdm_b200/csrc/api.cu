@@ -877,7 +877,8 @@ try {
         }
         uint64_t lo = lts1_index[f0] < iq_samples ? lts1_index[f0] : iq_samples;
         if (lo < copied) lo = copied;
-        const bool pull_this = iq_mapped && (pull_mode != 2 || (c & 1)); // mode 2: the DMA engine and the SMs share the link
+        const bool pull_this = iq_mapped && (pull_mode < 2 || (c % (uint32_t)pull_mode) != 0); // mode k >= 2: every k-th chunk goes
+                                                                                        // through the DMA engine, the rest is pulled
         cudaStream_t in_stream = pull_this ? h->pull_stream : h->copy_stream;
         if (pull_this) {
             CU(h, launch_pull(iq_mapped, S.d_iq, h->fmt, iq_samples, S.d_lts1 + f0, S.d_avail + f0, f1 - f0, h->sm_count,
@@ -886,7 +887,7 @@ try {
         } else if (hi > lo) {
             CU(h, cudaMemcpyAsync(S.d_iq + lo * bps, (const uint8_t *)iq + lo * bps, (size_t)(hi - lo) * bps,
                                   cudaMemcpyHostToDevice, in_stream));
-            if (pull_mode != 2) copied = hi;
+            if (pull_mode < 2) copied = hi;
         }
         cudaEvent_t ev_in = S.pipe_ev[2 * c], ev_out = S.pipe_ev[2 * c + 1];
         CU(h, cudaEventRecord(ev_in, in_stream));

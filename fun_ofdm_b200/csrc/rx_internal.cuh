@@ -219,7 +219,7 @@ struct Tuning {
     int acs_rn = ACS_RN_DEFAULT; // gen 2: renormalisation variant
     int h2d_chunk = 1024;   // b200rx_submit_batch: frames per pipelined chunk, and the size the last chunks shrink to
     int h2d_chunk_min = 256;
-    int pull_mode = -1;     // host-buffer ingest: 0 DMA copy, 1 GPU pull when the buffer is pinned, 2 alternate, -1 by format
+    int pull_mode = -1;     // host-buffer ingest: 0 DMA copy, 1 GPU pull when the buffer is pinned, k >= 2 every k-th chunk by DMA, -1 by format
     int inflight = 1;       // batches the caller keeps in flight on this handle (pipeline depth): the ACS launcher sizes its
                             // warps for the GPU being shared, not for one batch alone
     int scan_graph = 1;     // b200rx_pass_scan: replay the scan launches as a CUDA graph (1) or issue them one by one (0)

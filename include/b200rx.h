@@ -134,7 +134,8 @@ B200RX_API int b200rx_set_sample_format(b200rx_handle *h, int format, double sc1
  *   "acs_rn"        renormalisation variant: gen 2 cross-lane minimum in 1 (0) or 2 (1) lane bits per round; gen 3
  *                   subtract the minimum (0) or keep a per-frame offset (1, default)
  *   "h2d_chunk", "h2d_chunk_min"   frames per pipelined chunk of b200rx_submit_batch
- *   "pull_mode"     host-buffer ingest: 0 DMA copy, 1 GPU pull from pinned memory, 2 alternate, -1 by sample format
+ *   "pull_mode"     host-buffer ingest: 0 DMA copy, 1 GPU pull from pinned memory, k >= 2 every k-th chunk by DMA and the
+ *                   rest pulled, -1 by sample format (fc64: pull, narrower formats: DMA)
  *   "fe_split"      front end: 1 header kernel + data kernel with 8 lanes per OFDM symbol (default), 0 one CTA per frame
  *   "scan_graph"    b200rx_pass_scan: 1 replay the scan's launches as one CUDA graph (default), 0 issue them one by one
  * The call drains the handle first. */
