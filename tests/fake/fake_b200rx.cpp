@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -80,8 +81,22 @@ int b200rx_create(int, const b200rx_limits *limits, b200rx_handle **out)
 int b200rx_destroy(b200rx_handle *h) { delete h; return B200RX_OK; }
 const char *b200rx_last_error(const b200rx_handle *h) { return h ? h->error.c_str() : g_err.c_str(); }
 const char *b200rx_version(void) { return "fake b200rx (CPU test double over oracle/_ref)"; }
-int b200rx_host_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? B200RX_OK : B200RX_E_NOMEM; }
-int b200rx_host_free(void *p) { free(p); return B200RX_OK; }
+// "pinned" memory of the double: plain malloc, remembered so that b200rx_host_is_pinned can answer like the real library
+// (the chain copies long calls to the GPU straight from pinned caller buffers: that path is exercised on the CPU too)
+static std::vector<std::pair<char *, size_t> > g_pinned;
+int b200rx_host_alloc(void **p, size_t bytes)
+{
+    *p = malloc(bytes ? bytes : 1);
+    if (*p) g_pinned.push_back(std::make_pair((char *)*p, bytes ? bytes : 1));
+    return *p ? B200RX_OK : B200RX_E_NOMEM;
+}
+int b200rx_host_free(void *p)
+{
+    for (size_t i = 0; i < g_pinned.size(); i++)
+        if (g_pinned[i].first == (char *)p) { g_pinned.erase(g_pinned.begin() + i); break; }
+    free(p);
+    return B200RX_OK;
+}
 
 int b200rx_set_receive_origins(b200rx_handle *h, const int64_t *origins, uint32_t n)
 {
@@ -151,7 +166,12 @@ int b200rx_receive(b200rx_handle *h, const void *iq, uint64_t n, double, uint8_t
 // ---- two-phase passes: scan = the same capture logic, decode = hand out what the scan already computed ----
 int b200rx_set_pipeline_depth(b200rx_handle *, uint32_t) { return B200RX_OK; }
 int b200rx_set_tuning(b200rx_handle *, const char *, int64_t) { return B200RX_OK; }
-int b200rx_host_is_pinned(const void *) { return 0; }
+int b200rx_host_is_pinned(const void *p)
+{
+    for (size_t i = 0; i < g_pinned.size(); i++)
+        if ((const char *)p >= g_pinned[i].first && (const char *)p < g_pinned[i].first + g_pinned[i].second) return 1;
+    return 0;
+}
 int b200rx_set_sample_format(b200rx_handle *h, int fmt, double) { h->fmt = fmt; return B200RX_OK; }
 int b200rx_pass_open(b200rx_handle *h) { h->pass_iq.clear(); h->pass_raw.clear(); h->pass_frames = 0; return B200RX_OK; }
 int b200rx_pass_put(b200rx_handle *h, const void *iq, uint64_t n)

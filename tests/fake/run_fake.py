@@ -40,6 +40,13 @@ def main():
             got += ch.process(np.zeros(chunk, complex))
         c = ch.counters()
         ch.close()
+        # the same stream from a pinned caller buffer in long calls (copied to the GPU straight from it: no staging copy)
+        big = int(rng.choice([65536, 70001, 100000]))
+        want_big = _reference_chain(ref, x, big)
+        chp = Chain(max_frames=256, lib_path=FAKE_HOST)
+        got_big, _, _ = chp.run(x, big, pinned=True, max_out=512)
+        chp.close()
+        assert got_big == want_big, ("pinned direct path", s, big, len(got_big), len(want_big))
         out["chain"].append({"stream": s, "samples": len(x), "chunk": chunk, "snr": snr, "reference": [len(p) for p in want],
                              "adapter": [len(p) for p in got], "equal": got == want, "counters": c})
     # the block adapter on a synchronised stream (tests/test_gpu_block.py scenario)
