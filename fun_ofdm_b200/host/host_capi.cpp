@@ -4,6 +4,7 @@
 #include "b200_receiver_chain.h"
 #include "b200_receiver.h"
 
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <mutex>
@@ -231,7 +232,7 @@ API int b200host_receiver_run(const double *iq, long n, long chunk, long pause_a
         g_rx_rounds = 0;
     }
     const std::complex<double> *x = reinterpret_cast<const std::complex<double> *>(iq);
-    long pos = 0;
+    std::atomic<long> pos(0); // advanced by the receiver's thread, read by this one
     fun::b200_receiver::source_t source = [&](std::complex<double> *buf, size_t m) -> bool {
         if (pos >= n) return false;
         const long len = n - pos < (long)m ? n - pos : (long)m;
