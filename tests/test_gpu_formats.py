@@ -210,3 +210,69 @@ def test_submit_wait_overlapping_calls(ref, rx_factory):
         rx.wait(0)
         for p in pinned:
             lib.b200rx_host_free(p)
+
+
+@pytest.mark.parametrize("fmt_name", ["FMT_FC64", "FMT_FC32", "FMT_SC16"])
+def test_two_phase_pass_in_every_sample_format(ref, rx_factory, fmt_name):
+    """The pass entry points driven directly (open / put in two pieces / scan / decode / wait), graph-replayed scan and
+    launch-by-launch scan, for every raw sample format: frame list, header verdicts and decoded payloads must equal what
+    b200rx_receive returns for the same capture in the same format (which the other tests pin to the reference)."""
+    import fun_ofdm_b200 as fo
+    from fun_ofdm_b200.rx import SyncResult
+    from test_gpu_sync import _capture
+    fmt = getattr(fo, fmt_name)
+    rng = np.random.default_rng(600 + fmt)
+    rates = [int(r) for r in rng.integers(0, 11, 14)]
+    lengths = [int(v) for v in rng.integers(0, 500, 14)]
+    x, _ = _capture(ref, rng, rates, lengths, 40, gap=500, lead=300, tail=2048)
+    wire, scale, _ = narrow(x, fmt)
+    wire = np.ascontiguousarray(wire)
+    rx = rx_factory(32, 600)
+    rx.set_sample_format(fmt, scale)
+    want_payloads, info = rx.receive(wire)
+    nf = len(info["status"])
+    assert nf >= 10
+    L, h = rx.lib, rx.h
+    bps = {fo.FMT_FC64: 16, fo.FMT_FC32: 8, fo.FMT_SC16: 4}[fmt]
+    raw = wire.view(np.uint8).reshape(-1)
+    n = raw.size // bps
+    cut = n // 3
+
+    class PassFrame(C.Structure):
+        _fields_ = [("lts1", C.c_uint64), ("avail", C.c_uint32), ("length", C.c_uint16), ("rate", C.c_uint8), ("status", C.c_uint8),
+                    ("sts_end", C.c_uint64), ("phase", C.c_double)]
+    assert C.sizeof(PassFrame) == 32
+    try:
+        for graph in (1, 0):
+            rx.set_tuning("scan_graph", graph)
+            rx.set_pipeline_depth(2)
+            for rep in range(3):  # lanes are reused: the second pass on a lane replays its captured graph
+                frames = (PassFrame * 32)()
+                res = SyncResult()
+                assert L.b200rx_pass_open(h) == 0
+                assert L.b200rx_pass_put(h, raw.ctypes.data, cut) == 0
+                assert L.b200rx_pass_put(h, raw.ctypes.data + cut * bps, n - cut) == 0
+                assert L.b200rx_pass_scan(h, 0.0, frames, 32, C.byref(res)) == 0, L.b200rx_last_error(h)
+                assert res.n_frames == nf
+                for f in range(nf):
+                    assert frames[f].lts1 == int(info["lts1"][f])
+                    hdr_ok = info["status"][f] in (fo.ST_OK, fo.ST_CRC_FAIL)
+                    assert (frames[f].status == fo.ST_OK) == hdr_ok, (f, frames[f].status, info["status"][f])
+                    if hdr_ok:
+                        assert frames[f].length == int(info["length"][f]) and frames[f].rate == int(info["rate"][f])
+                sel = (C.c_uint8 * 32)(*[1 if frames[f].status == fo.ST_OK else 0 for f in range(nf)])
+                pl = np.zeros((32, 600), np.uint8)
+                st = np.full(32, 200, np.uint8)
+                t = C.c_uint64()
+                assert L.b200rx_pass_decode(h, sel, pl.ctypes.data, 600, st.ctypes.data, C.byref(t)) == 0 and t.value != 0
+                assert L.b200rx_pass_wait(h, t.value) == 0 and L.b200rx_pass_poll(h, t.value) == 1
+                got = [bytes(pl[f, : frames[f].length]) for f in range(nf) if sel[f] and st[f] == fo.ST_OK]
+                assert got == want_payloads, (fmt_name, graph, rep, len(got), len(want_payloads))
+                for f in range(nf):
+                    if sel[f]:
+                        assert st[f] == info["status"][f], (f, st[f], info["status"][f])
+            rx.synchronize()
+            rx.set_pipeline_depth(1)
+    finally:
+        rx.set_tuning("scan_graph", 1)
+        rx.set_sample_format(fo.FMT_FC64)
