@@ -9,7 +9,8 @@
  * receiver_chain::process_samples for a contiguous capture of raw samples.
  *
  * Plain pointers and sizes only; no C++/torch types; never throws; never keeps a caller pointer
- * after the call returns.  Every entry point returns 0 on success or a negative B200RX_E_* code;
+ * after the call returns, except where an entry point says so (the asynchronous ones: b200rx_submit_batch until
+ * b200rx_wait, b200rx_pass_put until b200rx_pass_scan, b200rx_pass_decode until b200rx_pass_wait).  Every entry point returns 0 on success or a negative B200RX_E_* code;
  * b200rx_last_error() gives the text.  There is NO CPU fallback: without a CUDA device of compute
  * capability 10.x b200rx_create() fails with B200RX_E_DEVICE.
  *
