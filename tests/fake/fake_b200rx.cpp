@@ -252,17 +252,30 @@ int b200rx_pass_scan(b200rx_handle *h, double phase_in, b200rx_pass_frame *frame
 int b200rx_pass_decode(b200rx_handle *h, const uint8_t *select, uint8_t *payload, uint32_t stride, uint8_t *status, uint64_t *ticket)
 {
     const uint32_t own = h->lim.max_payload_bytes ? h->lim.max_payload_bytes : 1;
+    static uint64_t next_ticket = 1;
     *ticket = 0;
     for (uint32_t f = 0; f < h->pass_frames; f++) {
         if (!select[f]) continue;
-        *ticket = 1;
+        if (*ticket == 0) *ticket = next_ticket++;
         status[f] = h->pass_status[f];
         if (payload && status[f] == B200RX_ST_OK)
             memcpy(payload + (size_t)f * stride, h->pass_payload.data() + (size_t)f * own, h->pass_len[f] < stride ? h->pass_len[f] : stride);
     }
     return B200RX_OK;
 }
-int b200rx_pass_poll(b200rx_handle *, uint64_t) { return 1; }
+// B200RX_FAKE_SLOW_POLLS=k: a pass reports "still running" to its first k polls (a wait always completes it) - lets the
+// CPU tests see the adapters' delivery-lag rules, which a double that finishes instantly would never exercise
+static int g_polls_left = -1;
+int b200rx_pass_poll(b200rx_handle *, uint64_t ticket)
+{
+    if (ticket == 0) return 1;
+    static uint64_t cur = 0;
+    static int left = 0;
+    if (g_polls_left < 0) { const char *e = getenv("B200RX_FAKE_SLOW_POLLS"); g_polls_left = e ? atoi(e) : 0; }
+    if (ticket != cur) { cur = ticket; left = g_polls_left; }
+    if (left > 0) { left--; return 0; }
+    return 1;
+}
 int b200rx_pass_wait(b200rx_handle *, uint64_t) { return B200RX_OK; }
 
 } // extern "C"

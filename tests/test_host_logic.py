@@ -48,6 +48,26 @@ def test_adapters_match_reference_on_chunked_streams(fake_built, seed):
         assert b["equal"], b
 
 
+def test_delivery_lag_rules(fake_built):
+    """fun::b200_receiver_chain hands a payload out as soon as its pass has finished and never later than max_lag calls
+    after the call that completed the frame (the reference's own chain: five).  A CPU double whose passes never finish
+    on their own shows the bound (lag == max_lag for every frame, 0 for the synchronous chain), one whose passes finish
+    at once shows the floor (the next call); nothing is lost, flush() has nothing left to return."""
+    def run(slow_polls):
+        r = subprocess.run([sys.executable, os.path.join(FAKE, "run_lag.py"), str(slow_polls)], capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    never = run(10 ** 9)
+    for key, lag in (("6/5", 5), ("4/2", 2), ("8/7", 7), ("1/0", 0)):
+        assert never[key]["payloads"] == 12 and never[key]["left_for_flush"] == 0, never[key]
+        assert never[key]["lags"] == [lag] * 12, (key, never[key]["lags"])
+    at_once = run(0)
+    for key in ("6/5", "4/2", "8/7"):
+        assert at_once[key]["payloads"] == 12 and set(at_once[key]["lags"]) <= {1}, (key, at_once[key])
+    assert at_once["1/0"]["lags"] == [0] * 12
+
+
 def test_fake_library_is_test_only():
     """the test double must never be reachable from the product tree"""
     for base, _, files in os.walk(os.path.join(ROOT, "fun_ofdm_b200")):
