@@ -42,6 +42,23 @@ def main():
         done_call = [int(e // chunk) for e in ends]
         lags = [a - d for a, d in zip(arrival, done_call)]
         out["%d/%d" % (depth, lag)] = {"payloads": len(arrival) + len(tail), "lags": lags, "left_for_flush": len(tail)}
+    # the block adapter on the same stream with genie tags (LTS1 at frame start + 184), rounds of 4096 samples
+    from test_gpu_block import Block
+    tags = np.zeros(len(x), np.uint8)
+    starts = np.cumsum([gap + len(f) for f in frames]) - np.array([len(f) for f in frames])
+    tags[starts + 184] = 4
+    for depth, lag in ((4, 3), (6, 1), (1, 0)):
+        blk = Block(max_frames=64, lib_path=FAKE_HOST, depth=depth, max_lag=lag)
+        arrival = []
+        for c, pos in enumerate(range(0, len(x), chunk)):
+            got = blk.work(x[pos: pos + chunk], tags[pos: pos + chunk])
+            arrival += [c] * len(got)
+        tail = blk.work(np.zeros(1, complex), np.zeros(1, np.uint8), flush=True)
+        blk.close()
+        # complete when sample LTS1 + 128 + 80 * (1 + nsym) - 1 has arrived: the frame's last sample
+        done_call = [int(e // chunk) for e in ends]
+        out["block %d/%d" % (depth, lag)] = {"payloads": len(arrival) + len(tail), "lags": [a - d for a, d in zip(arrival, done_call)],
+                                            "left_for_flush": len(tail)}
     print(json.dumps(out), flush=True)
     os._exit(0)
 

@@ -62,6 +62,9 @@ def test_delivery_lag_rules(fake_built):
     for key, lag in (("6/5", 5), ("4/2", 2), ("8/7", 7), ("1/0", 0)):
         assert never[key]["payloads"] == 12 and never[key]["left_for_flush"] == 0, never[key]
         assert never[key]["lags"] == [lag] * 12, (key, never[key]["lags"])
+    for key, lag in (("block 4/3", 3), ("block 6/1", 1), ("block 1/0", 0)):  # fun::b200_rx: rounds instead of calls
+        assert never[key]["payloads"] == 12 and never[key]["left_for_flush"] == 0, never[key]
+        assert never[key]["lags"] == [lag] * 12, (key, never[key]["lags"])
     at_once = run(0)
     for key in ("6/5", "4/2", "8/7"):
         assert at_once[key]["payloads"] == 12 and set(at_once[key]["lags"]) <= {1}, (key, at_once[key])
