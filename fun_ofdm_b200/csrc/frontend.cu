@@ -668,7 +668,8 @@ cudaError_t launch_frontend_data(const FrontendArgs &a, cudaStream_t s)
 cudaError_t launch_frontend(const FrontendArgs &a, cudaStream_t s)
 {
     if (a.n_frames == 0) return cudaSuccess;
-    const dim3 grid(a.n_frames), block(FE_WARPS * 32);
+    // the header pass only has work for two warps (LTS1 / LTS2, then SIGNAL on warp 0): half-size CTAs, twice as many resident
+    const dim3 grid(a.n_frames), block(a.header_only ? 64 : FE_WARPS * 32);
     const bool dbg = a.dbg_eq != nullptr || a.dbg_depunct != nullptr;
 #define FE_LAUNCH(ROTV, FMTV) do { if (dbg) frontend_kernel<ROTV, FMTV, true><<<grid, block, 0, s>>>(a); \
                                    else frontend_kernel<ROTV, FMTV, false><<<grid, block, 0, s>>>(a); } while (0)
